@@ -1,0 +1,28 @@
+# Builds the C-ABI CUDA library (sm_100a only) in-tree so the .so travels with the repo snapshot.
+NVCC      ?= nvcc
+PKG       := semantic_pyramid_for_image_generation_b200
+CSRC      := $(PKG)/csrc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+LIB       := $(PKG)/libspyramid_b200.so
+
+all: $(LIB)
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/spyramid_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+native_tests: $(LIB) build/test_conv_native
+
+build/test_conv_native: tests/native/test_conv_native.cu $(LIB)
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all native_tests clean
