@@ -237,13 +237,13 @@ int main(int argc, char** argv) {
   }
   if (!strcmp(mode, "all") || !strcmp(mode, "wgrad")) {
     fails += test_wgrad(2, 16, 16, 64, 64, 3, 0, 0, 1);
-    fails += test_wgrad(2, 16, 16, 64, 64, 3, 1024, 8192, 1);  // alternative descriptor hypothesis
     fails += test_wgrad(2, 16, 16, 64, 64, 1, 0, 0, 2);
     fails += test_wgrad(2, 16, 16, 128, 128, 3, 0, 0, 0);
-    fails += test_wgrad(2, 16, 16, 128, 128, 3, 1024, 8192, 0);
     fails += test_wgrad(3, 8, 8, 128, 256, 3, 0, 0, 0);
     fails += test_wgrad(5, 4, 4, 64, 512, 3, 0, 0, 0);
     fails += test_wgrad(2, 32, 32, 256, 32, 1, 0, 0, 0);
+    fails += test_wgrad(2, 64, 64, 64, 64, 3, 0, 0, 0);
+    fails += test_wgrad(20, 1, 1, 512, 128, 1, 0, 0, 0);
   }
   printf("native conv tests: %d failure(s)\n", fails);
   return fails ? 1 : 0;

@@ -1,0 +1,204 @@
+"""Pins oracle/spyramid_oracle.py against the UNMODIFIED reference (imported through shims) on CPU.
+
+Runs only where /root/reference exists (the build container); on the GPU box the committed goldens in
+tests/golden/ (generated from the reference by tests/golden/make_golden.py) take over (test_golden.py).
+"""
+import copy
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_shims
+from oracle import spyramid_oracle as O
+
+pytestmark = pytest.mark.skipif(not reference_shims.reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return reference_shims.import_reference()
+
+
+def _clone(sd):
+    return {k: v.clone() for k, v in sd.items()}
+
+
+def test_state_dict_keys_and_shapes_match_reference(ref):
+    models, _, _ = ref
+    for cf in (1, 2):
+        g = models.Generator(channels_factor=cf)
+        d = models.Discriminator(channel_factor=cf)
+        for module, mine in ((g, O.init_generator_state(cf)), (d, O.init_discriminator_state(cf))):
+            theirs = module.state_dict()
+            assert list(theirs.keys()) == list(mine.keys())
+            for k in theirs:
+                assert tuple(theirs[k].shape) == tuple(mine[k].shape), k
+    v = models.VGG16()
+    mine = O.init_vgg_state()
+    theirs = v.state_dict()
+    assert set(theirs.keys()) == set(mine.keys())
+    for k in theirs:
+        assert tuple(theirs[k].shape) == tuple(mine[k].shape), k
+
+
+def test_vgg_features_match_reference(ref):
+    models, _, _ = ref
+    sd = O.init_vgg_state(seed=5)
+    v = models.VGG16()
+    v.load_state_dict(sd)
+    v.eval()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    with torch.no_grad():
+        theirs = v(x)
+        mine = O.vgg16_features(sd, x)
+    assert [tuple(t.shape) for t in theirs] == [tuple(t.shape) for t in mine]
+    for a, b in zip(theirs, mine):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert float(theirs[5].min()) == 0.0  # fc7 tap is post-ReLU
+
+
+@pytest.mark.parametrize("cf", [1, 2])
+def test_generator_discriminator_forward_and_state_match_reference(ref, cf):
+    models, _, _ = ref
+    g_sd, d_sd = O.init_generator_state(cf, seed=3), O.init_discriminator_state(cf, seed=4)
+    g, d = models.Generator(channels_factor=cf), models.Discriminator(channel_factor=cf)
+    g.load_state_dict(_clone(g_sd))
+    d.load_state_dict(_clone(d_sd))
+    g.train()
+    d.train()
+    images, labels, masks, z, _ = O.synthetic_batch(3, seed=1, mask_mode="blob")
+    feats = O.vgg16_features(O.init_vgg_state(seed=5), images)
+    with torch.no_grad():
+        for _ in range(2):  # two forwards: power iteration / running stats advance identically
+            theirs = g(input=z, features=feats, masks=masks, class_id=labels.float())
+            mine = O.generator_forward(g_sd, z, feats, masks, labels.float(), training=True)
+            assert torch.allclose(theirs, mine, rtol=1e-4, atol=1e-5)
+            p_theirs = d(theirs, labels)
+            p_mine = O.discriminator_forward(d_sd, mine, labels, training=True)
+            assert p_theirs.shape == (3, 3, 128) and p_mine.shape == (3, 3, 128)
+            assert torch.allclose(p_theirs, p_mine, rtol=1e-4, atol=1e-5)
+    for module, sd in ((g, g_sd), (d, d_sd)):
+        for k, t in module.state_dict().items():
+            assert torch.allclose(t.float(), sd[k].float(), rtol=1e-4, atol=1e-6), k
+    # eval mode: no power iteration, running statistics
+    g.eval()
+    with torch.no_grad():
+        theirs = g(input=z, features=feats, masks=masks, class_id=labels.float())
+        mine = O.generator_forward(g_sd, z, feats, masks, labels.float(), training=False)
+    assert torch.allclose(theirs, mine, rtol=1e-4, atol=1e-5)
+
+
+def test_losses_match_reference(ref):
+    _, lossfunction, _ = ref
+    gen = torch.Generator().manual_seed(0)
+    fr = [torch.randn(2, 8, 16, 16, generator=gen), torch.randn(2, 4096, generator=gen)]
+    ff = [torch.randn(2, 8, 16, 16, generator=gen), torch.randn(2, 4096, generator=gen)]
+    ms = [(torch.rand(2, 1, 16, 16, generator=gen) > 0.5).float(), torch.ones(2, 4096)]
+    assert torch.allclose(lossfunction.SemanticReconstructionLoss()(fr, ff, ms),
+                          O.semantic_reconstruction_loss(fr, ff, ms))
+    img, z = torch.randn(4, 3, 8, 8, generator=gen), torch.randn(4, 128, generator=gen)
+    assert torch.allclose(lossfunction.DiversityLoss()(img, z), O.diversity_loss(img, z))
+    p, q = torch.randn(4, 4, 128, generator=gen), torch.randn(4, 4, 128, generator=gen)
+    assert torch.allclose(lossfunction.LSGANGeneratorLoss()(p), O.lsgan_generator_loss(p))
+    a, b = lossfunction.LSGANDiscriminatorLoss()(p, q)
+    c, d = O.lsgan_discriminator_loss(p, q)
+    assert torch.allclose(a, c) and torch.allclose(b, d)
+
+
+def test_full_train_step_matches_reference(ref):
+    """model_wrapper.py:136-190 executed with the reference modules vs oracle.train_step (B=2, config 1)."""
+    models, lossfunction, _ = ref
+    g_sd, d_sd, v_sd = O.init_generator_state(2, seed=3), O.init_discriminator_state(2, seed=4), O.init_vgg_state(5)
+    g, d, v = models.Generator(channels_factor=2), models.Discriminator(channel_factor=2), models.VGG16()
+    g.load_state_dict(_clone(g_sd))
+    d.load_state_dict(_clone(d_sd))
+    v.load_state_dict(_clone(v_sd))
+    g.train(); d.train(); v.eval()
+    for p in v.parameters():
+        p.requires_grad = False
+    g_opt = torch.optim.Adam(g.parameters(), lr=1e-5)
+    d_opt = torch.optim.Adam(d.parameters(), lr=1e-5)
+    images, labels, masks, z_d, z_g = O.synthetic_batch(2, seed=0, mask_mode="inference")
+    # --- the reference step body, verbatim order ---
+    g.zero_grad(); d.zero_grad()
+    with torch.no_grad():
+        features_real = v(images)
+        images_fake = g(input=z_d, features=features_real, masks=masks, class_id=labels.float())
+    prediction_real = d(images, labels)
+    prediction_fake = d(images_fake, labels)
+    l_real, l_fake = lossfunction.LSGANDiscriminatorLoss()(prediction_real, prediction_fake)
+    (l_real + l_fake).backward()
+    d_grads_ref = {k: p.grad.clone() for k, p in d.named_parameters()}
+    d_opt.step()
+    g.zero_grad(); d.zero_grad()
+    images_fake = g(input=z_g, features=features_real, masks=masks, class_id=labels.float())
+    prediction_fake = d(images_fake, labels)
+    l_g = lossfunction.LSGANGeneratorLoss()(prediction_fake)
+    l_div = 0.1 * lossfunction.DiversityLoss()(images_fake, z_g)
+    features_fake = v(images_fake)
+    l_rec = 0.1 * lossfunction.SemanticReconstructionLoss()(features_real, features_fake, masks)
+    (l_g + l_rec + l_div).backward()
+    g_grads_ref = {k: p.grad.clone() for k, p in g.named_parameters()}
+    g_opt.step()
+    # --- oracle ---
+    out = O.train_step(g_sd, d_sd, v_sd, images, labels, masks, z_d, z_g, {}, {}, lr=1e-5)
+    assert out["loss_discriminator_real"] == pytest.approx(float(l_real), rel=1e-4)
+    assert out["loss_discriminator_fake"] == pytest.approx(float(l_fake), rel=1e-3, abs=1e-7)
+    assert out["loss_generator"] == pytest.approx(float(l_g), rel=1e-4)
+    assert out["loss_generator_semantic_reconstruction"] == pytest.approx(float(l_rec), rel=1e-4)
+    assert out["loss_generator_diversity"] == pytest.approx(float(l_div), rel=1e-4)
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-20))
+
+    for k, gref in d_grads_ref.items():
+        if float(gref.abs().max()) > 1e-7:  # skips analytically-zero grads (bias feeding a BatchNorm)
+            tol = 3e-2 if gref.numel() == 1 else 2e-3
+            assert rel(out["d_grads"][k], gref) < tol, (k, rel(out["d_grads"][k], gref))
+    for k, gref in g_grads_ref.items():
+        if float(gref.abs().max()) > 1e-7:  # skips analytically-zero grads (bias feeding a BatchNorm)
+            tol = 3e-2 if gref.numel() == 1 else 2e-3  # scalar gamma: one fp32 sum with heavy cancellation
+            assert rel(out["g_grads"][k], gref) < tol, (k, rel(out["g_grads"][k], gref))
+    # Adam's first step moves every weight by ~lr*sign(g): entries whose gradient is at rounding-noise level may
+    # flip sign between two fp32 evaluations, so post-step parameters agree to 2*lr, buffers (u, v, BN) tightly.
+    for module, sd in ((g, g_sd), (d, d_sd)):
+        for k, t in module.state_dict().items():
+            atol = 2.5e-5 if k in O.trainable_keys(sd) else 2e-6
+            assert torch.allclose(t.float(), sd[k].float(), rtol=1e-3, atol=atol), k
+
+
+def test_masks_bit_exact(ref):
+    _, _, misc = ref
+    for stage in range(7):
+        for a, b in zip(misc.get_masks_for_inference(stage), O.masks_for_inference(stage)):
+            assert torch.equal(a, b)
+    # training masks: same RNG consumption and selection logic; the rasteriser is injected on both sides
+    rng = np.random.RandomState(7)
+    canned = {}
+
+    def shape_image(hw, min_size):
+        key = (hw, min_size, len(canned))
+        img = np.full(hw, 255, dtype=np.uint8)
+        y, x = rng.randint(0, hw[0] // 2), rng.randint(0, hw[1] // 2)
+        img[y:y + max(min_size, 2), x:x + max(min_size, 2)] = rng.randint(0, 200)
+        canned[key] = img
+        return img
+
+    def fake_random_shapes(shape, min_shapes, max_shapes, min_size, allow_overlap):
+        img = shape_image(tuple(shape), min_size)
+        return np.stack([img, img, img], axis=-1), None
+
+    misc.random_shapes = fake_random_shapes
+    n_spatial = 0
+    for seed in range(60):
+        random.seed(seed); np.random.seed(seed); rng.seed(seed)
+        theirs = misc.get_masks_for_training()
+        random.seed(seed); np.random.seed(seed); rng.seed(seed)
+        mine = O.masks_for_training(shape_image)
+        assert len(theirs) == len(mine) == 7
+        for a, b in zip(theirs, mine):
+            assert a.shape == b.shape and torch.equal(a, b)
+        n_spatial += int(any(0 < float(m.mean()) < 1 for m in mine))
+    assert n_spatial > 0
