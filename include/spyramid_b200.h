@@ -42,8 +42,13 @@ void spyr_launch_count_reset(void);
 typedef struct {
   const void* x;  /* NHWC bf16 [B,H,W,cin] */
   const void* w;  /* bf16 [ksize*ksize][Cout][cin] */
-  int cin;        /* multiple of 8 */
+  int cin;        /* reduction channels of this source, multiple of 8 */
   int ksize;      /* 1 or 3 */
+  int w_mn_major; /* 0: w is [taps][Cout][cin] (fprop pack).  1: input-gradient mode -- w is the SAME fprop pack of
+                     the forward conv, read as [taps][cin][Cout] with Cout (the forward conv's Cin) contiguous
+                     (UMMA MN-major B operand) and the taps flipped: out[p] = sum_t x[p + d_t] * w[8 - t] */
+  int w_per_image;/* 1: ksize must be 1; image b uses weight slice w[b] (batched GEMM for SAGAN attention,
+                     models.py:266-268) */
 } spyr_conv_src;
 
 typedef struct {
@@ -61,6 +66,7 @@ typedef struct {
   int act;                    /* 0 none, 1 relu, 2 leaky-relu(act_slope) */
   float act_slope;
   float* y_f32;               /* f32 [B*H*W][Cout] accumulate target or NULL */
+  int f32_store;              /* 1: plain store of the accumulator to y_f32 (splits must be 1; no zero-fill needed) */
   int splits;                 /* >=1; >1 requires y_f32 */
   int block_n;                /* 0 = auto, else 32..256 multiple of 16 */
   int stages;                 /* 0 = auto */
@@ -78,6 +84,7 @@ typedef struct {
   float* dw;       /* f32 [taps][Cin][Cout]  */
   int splits;      /* 0 = auto */
   int stages;      /* 0 = auto */
+  int per_image;   /* 1: one dw slice per image, dw is f32 [B][taps][Cin][Cout] (attention dK/dV, models.py:266-268) */
   /* debug/validation knobs for the UMMA MN-major descriptors; 0 = defaults */
   int dbg_lbo, dbg_sbo;
 } spyr_wgrad_desc;

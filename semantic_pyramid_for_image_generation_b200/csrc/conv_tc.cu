@@ -33,6 +33,10 @@ struct FpropParams {
   int ktaps[3];    // taps per source (1 or 9)
   int kchunks[3];  // ceil(cin/64) per source
   int ktotal;      // total k-steps
+  int wmn[3];      // source uses the MN-major (input-gradient) weight view
+  int wpi[3];      // source uses per-image weights
+  int b_bytes;     // bytes reserved for the B tile per stage
+  int f32_store;
   int block_n;
   int stages;
   int splits;
@@ -60,8 +64,8 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB | B block_n*128] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.block_n * KC * 2;
-  const int stage_bytes = A_BYTES + b_bytes;
+  const int stage_bytes = A_BYTES + p.b_bytes;
+  const int b_chunks = (p.block_n + 63) >> 6;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -125,14 +129,22 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * stage_bytes;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const uint32_t b_tx = p.wmn[s] ? (uint32_t)(b_chunks * 8192) : (uint32_t)(p.block_n * KC * 2);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)A_BYTES + b_tx);
           int dy = 0, dx = 0;
           if (p.ktaps[s] == 9) {
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
           tma_load_4d(a_dst, &maps.x[s], &full_bar[stage], chunk * KC, w0 + dx, h0 + dy, n0);
-          tma_load_3d(b_dst, &maps.w[s], &full_bar[stage], chunk * KC, n_off, tap);
+          if (p.wmn[s]) {
+            // input-gradient view: B[k = forward cout][n = forward cin], n contiguous, taps flipped
+            const int wtap = p.wpi[s] ? n0 : (p.ktaps[s] == 9 ? 8 - tap : 0);
+            for (int j = 0; j < b_chunks; ++j)
+              tma_load_3d(b_dst + j * 8192, &maps.w[s], &full_bar[stage], n_off + j * 64, chunk * KC, wtap);
+          } else {
+            tma_load_3d(b_dst, &maps.w[s], &full_bar[stage], chunk * KC, n_off, p.wpi[s] ? n0 : tap);
+          }
           if (++chunk == p.kchunks[s]) {
             chunk = 0;
             if (++tap == p.ktaps[s]) {
@@ -148,10 +160,17 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
       }
     } else if (warp == 1) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+      const uint32_t idesc_k = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+      const uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 1);
       int stage = 0;
       uint32_t phase = 0;
+      int s = 0, s_end = p.ktaps[0] * p.kchunks[0];
       for (int it = k_begin; it < k_end; ++it) {
+        while (it >= s_end && s < p.nsrc - 1) {
+          ++s;
+          s_end += p.ktaps[s] * p.kchunks[s];
+        }
+        const bool mn = p.wmn[s] != 0;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -160,8 +179,11 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
             const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (it > k_begin || k > 0) ? 1u : 0u);
+            // K-major B: 16 channels = 32 B along the swizzled row.  MN-major B: 16 k-rows of 128 B = 2 KB,
+            // 64-column chunks 8 KB apart (LBO), 8-row swizzle atoms 1 KB apart (SBO).
+            const uint64_t db = mn ? umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                   : umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(tmem_base, da, db, mn ? idesc_mn : idesc_k, (it > k_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (it == k_end - 1) umma_commit(tmem_full_bar);
@@ -211,6 +233,19 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
         if (col0 >= p.Cout) continue;
         if (p.y_f32 != nullptr) {
           float* dst = p.y_f32 + pix * p.Cout + col0;
+          if (p.f32_store) {
+            if (col0 + 32 <= p.Cout && (p.Cout & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Cout) dst[j] = __uint_as_float(r[j]);
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -309,6 +344,7 @@ struct WgradParams {
   int splits;
   uint32_t tmem_cols;
   uint32_t lbo, sbo;
+  int per_image;    // splits per image when > 0 (dw gets one slice per image)
   float* dw;
 };
 
@@ -337,6 +373,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   const int per = (p.ptiles + p.splits - 1) / p.splits;
   const int k_begin = blockIdx.z * per;
   const int k_end = min(p.ptiles, k_begin + per);
+  float* dw_out = p.dw;
+  if (p.per_image > 0) dw_out += (size_t)(blockIdx.z / p.per_image) * p.taps * p.Cin * p.Cout;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x);
@@ -442,7 +480,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         tmem_ld_wait();
         if (!valid) continue;
         const int col0 = n_off + c0;
-        float* dst = p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + col0;
+        float* dst = dw_out + ((size_t)tap * p.Cin + ci) * p.Cout + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -502,7 +540,10 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   const bool f32_out = d->y_f32 != nullptr;
   SPYR_REQUIRE(f32_out || (d->Cout % 8 == 0), "conv2d_fprop: bf16 output needs Cout %% 8 == 0 (Cout=%d)", d->Cout);
   SPYR_REQUIRE(d->splits <= 1 || f32_out, "conv2d_fprop: split-K needs y_f32");
+  SPYR_REQUIRE(!d->f32_store || (f32_out && d->splits <= 1), "conv2d_fprop: f32_store needs y_f32 and splits<=1");
   p.splits = d->splits < 1 ? 1 : d->splits;
+  p.f32_store = d->f32_store;
+  p.b_bytes = bn * KC * 2;
 
   TmapPack maps;
   p.ktotal = 0;
@@ -514,14 +555,26 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
     p.ktaps[s] = src.ksize * src.ksize;
     p.kchunks[s] = ceil_div(src.cin, KC);
     p.ktotal += p.ktaps[s] * p.kchunks[s];
+    p.wmn[s] = src.w_mn_major ? 1 : 0;
+    p.wpi[s] = src.w_per_image ? 1 : 0;
+    SPYR_REQUIRE(!src.w_per_image || (src.ksize == 1 && p.TN == 1),
+                 "conv2d_fprop: per-image weights need ksize 1 and H*W >= 128");
+    SPYR_REQUIRE(!src.w_mn_major || (d->Cout % 8 == 0), "conv2d_fprop: MN-major weights need Cout %% 8 == 0");
+    if (src.w_mn_major && ceil_div(bn, 64) * 8192 > p.b_bytes) p.b_bytes = ceil_div(bn, 64) * 8192;
     {
       uint64_t dims[4] = {(uint64_t)src.cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
       uint64_t strides[3] = {(uint64_t)src.cin * 2, (uint64_t)d->W * src.cin * 2, (uint64_t)d->H * d->W * src.cin * 2};
       uint32_t box[4] = {KC, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
       if (spyr_tmap_encode(&maps.x[s], src.x, 4, dims, strides, box, 1)) return 3;
     }
-    {
-      uint64_t dims[3] = {(uint64_t)src.cin, (uint64_t)d->Cout, (uint64_t)p.ktaps[s]};
+    const uint64_t wslices = src.w_per_image ? (uint64_t)d->B : (uint64_t)p.ktaps[s];
+    if (src.w_mn_major) {
+      uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)src.cin, wslices};
+      uint64_t strides[2] = {(uint64_t)d->Cout * 2, (uint64_t)d->Cout * src.cin * 2};
+      uint32_t box[3] = {64, KC, 1};
+      if (spyr_tmap_encode(&maps.w[s], src.w, 3, dims, strides, box, 1)) return 3;
+    } else {
+      uint64_t dims[3] = {(uint64_t)src.cin, (uint64_t)d->Cout, wslices};
       uint64_t strides[2] = {(uint64_t)src.cin * 2, (uint64_t)d->Cout * src.cin * 2};
       uint32_t box[3] = {KC, (uint32_t)bn, 1};
       if (spyr_tmap_encode(&maps.w[s], src.w, 3, dims, strides, box, 1)) return 3;
@@ -532,7 +585,7 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
     maps.w[s] = maps.w[0];
   }
   if (p.splits > p.ktotal) p.splits = p.ktotal;
-  const int stage_bytes = A_BYTES + bn * KC * 2;
+  const int stage_bytes = A_BYTES + p.b_bytes;
   int stages = d->stages;
   if (stages == 0) {
     stages = (bn > 128) ? 4 : (96 * 1024) / stage_bytes;
@@ -595,6 +648,14 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
     if (splits < 1) splits = 1;
   }
   if (splits > p.ptiles) splits = p.ptiles;
+  if (d->per_image) {
+    const int tpi = p.tiles_w * p.tiles_h;  // pixel tiles per image
+    SPYR_REQUIRE(p.TN == 1 && p.tiles_n == d->B, "conv2d_wgrad: per_image needs H*W >= 64");
+    int s = 1;
+    while (s * 2 <= tpi && tpi % (s * 2) == 0 && mtiles * ntiles * d->B * s * 2 <= 2 * 148) s *= 2;
+    p.per_image = s;
+    splits = d->B * s;
+  }
   p.splits = splits;
   const int stage_bytes = (2 + bn / 64) * KP * 128;
   int stages = d->stages;

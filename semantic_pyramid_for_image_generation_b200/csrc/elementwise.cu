@@ -1,0 +1,854 @@
+// Bandwidth-bound glue of the training step: one coalesced, 16-byte-vectorised pass each.
+// Feature maps are NHWC BF16 (8 channels = one uint4 per thread); images are NCHW FP32 as the reference's
+// data loader delivers them (data.py:76-90).
+//
+// Replaces the ATen elementwise / pooling / interpolation calls of the reference:
+//   kornia.normalize (models.py:195-197), nn.MaxPool2d (models.py:203,245), nn.AvgPool2d (models.py:406,451),
+//   nn.AdaptiveAvgPool2d (models.py:126,206), feature*mask and torch.cat (models.py:78-94), gamma*o+x (models.py:274),
+//   the final 1x1 conv + tanh (models.py:58-61,99).
+#include "common.cuh"
+#include "../../include/spyramid_b200.h"
+
+extern void spyr_count_launch();
+
+namespace {
+
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3-channel image <-> 32-wide im2col rows (k = tap*3 + c, taps row-major over (dy,dx), 27..31 zero)
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col3x3_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, bf16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)B * H * W;
+  if (idx >= npix) return;
+  const int w = (int)(idx % W);
+  const int h = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long long)W * H));
+  float m[3] = {0.f, 0.f, 0.f}, is[3] = {1.f, 1.f, 1.f};
+  if (mean != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      m[c] = mean[c];
+      is[c] = invstd[c];
+    }
+  }
+  float v[32];
+#pragma unroll
+  for (int i = 27; i < 32; ++i) v[i] = 0.f;
+  const float* base = img + (size_t)b * 3 * H * W;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+    const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[t * 3 + c] = in ? (__ldg(base + ((size_t)c * H + hh) * W + ww) - m[c]) * is[c] : 0.f;
+  }
+  bf16* dst = out + idx * 32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) st8(dst + g * 8, v + g * 8);
+}
+
+__global__ void col2im3x3_kernel(const bf16* __restrict__ gcol, int B, int H, int W, const float* __restrict__ invstd,
+                                 float* __restrict__ gimg, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)B * H * W;
+  if (idx >= npix) return;
+  const int w = (int)(idx % W);
+  const int h = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long long)W * H));
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    // col[p][t] = img[p + d_t]  =>  gimg[q] += gcol[q - d_t][t]
+    const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const bf16* src = gcol + (((size_t)b * H + hh) * W + ww) * 32 + t * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += __bfloat162float(src[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = acc[c];
+    if (invstd != nullptr) v *= invstd[c];
+    float* dst = gimg + (((size_t)b * 3 + c) * H + h) * W + w;
+    *dst = accumulate ? (*dst + v) : v;
+  }
+}
+
+// (B,3,H,W) f32 -> 2x2 average -> (B,H/2,W/2,8) bf16 (channels 3..7 zero): input of the D input block's skip conv
+__global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, int H, int W, bf16* __restrict__ out) {
+  const int OH = H / 2, OW = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW) return;
+  const int w = (int)(idx % OW);
+  const int h = (int)((idx / OW) % OH);
+  const int b = (int)(idx / ((long long)OW * OH));
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = img + (((size_t)b * 3 + c) * H + 2 * h) * W + 2 * w;
+    v[c] = 0.25f * (p[0] + p[1] + p[W] + p[W + 1]);
+  }
+  st8(out + idx * 8, v);
+}
+__global__ void img_avgpool_pad8_bwd_kernel(const bf16* __restrict__ g8, int B, int H, int W, float* __restrict__ gimg,
+                                            int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W) return;
+  const int w = (int)(idx % W);
+  const int h = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long long)W * H));
+  const bf16* src = g8 + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * 8;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = 0.25f * __bfloat162float(src[c]);
+    float* dst = gimg + (((size_t)b * 3 + c) * H + h) * W + w;
+    *dst = accumulate ? (*dst + v) : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW f32 <-> NHWC bf16 (API boundary only), optional per-pixel mask gate
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ mask, bf16* __restrict__ dst,
+                                    int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((size_t)b * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      float v = tile[threadIdx.x][i];
+      if (mask != nullptr) v *= mask[(size_t)b * HW + p];
+      dst[((size_t)b * HW + p) * C + c] = __float2bfloat16(v);
+    }
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[((size_t)b * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void maskgate_kernel(const bf16* __restrict__ f, const float* __restrict__ mask, bf16* __restrict__ out,
+                                long long npix, int cg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * cg) return;
+  const long long pix = idx / cg;
+  float v[8];
+  ld8(f + idx * 8, v);
+  const float m = __ldg(mask + pix);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= m;
+  st8(out + idx * 8, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual, bf16* __restrict__ y_raw,
+                                    bf16* __restrict__ y_act, float slope, int B, int H, int W, int cg) {
+  const int OH = H / 2, OW = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % OW);
+  t /= OW;
+  const int h = (int)(t % OH);
+  const int b = (int)(t / OH);
+  const size_t C = (size_t)cg * 8;
+  const bf16* p = x + (((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8;
+  float a[8], v[8];
+  ld8(p, v);
+  ld8(p + C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += a[j];
+  ld8(p + (size_t)W * C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += a[j];
+  ld8(p + (size_t)W * C + C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.25f * (v[j] + a[j]);
+  if (residual != nullptr) {
+    ld8(residual + idx * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += a[j];
+  }
+  if (y_raw != nullptr) st8(y_raw + idx * 8, v);
+  if (y_act != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = lrelu_f(v[j], slope);
+    st8(y_act + idx * 8, v);
+  }
+}
+// g_hi[b,h,w,:] = 0.25 * g_lo[b,h/2,w/2,:]   (H, W are the high-resolution dims)
+__global__ void avgpool2_bwd_kernel(const bf16* __restrict__ g_lo, bf16* __restrict__ g_hi, int B, int H, int W, int cg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % W);
+  t /= W;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  float v[8];
+  ld8(g_lo + ((((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * cg + c) * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
+  st8(g_hi + idx * 8, v);
+}
+
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int cg) {
+  const int OH = H / 2, OW = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % OW);
+  t /= OW;
+  const int h = (int)(t % OH);
+  const int b = (int)(t / OH);
+  const size_t C = (size_t)cg * 8;
+  const bf16* p = x + (((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8;
+  float a[8], v[8];
+  ld8(p, v);
+  ld8(p + C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], a[j]);
+  ld8(p + (size_t)W * C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], a[j]);
+  ld8(p + (size_t)W * C + C, a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], a[j]);
+  st8(y + idx * 8, v);
+}
+// routes gy to the FIRST maximum of each 2x2 window in (row, col) scan order (ATen max_pool2d backward),
+// optionally gated by x > 0 (the ReLU that produced x).
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy, bf16* __restrict__ gx, int B,
+                                    int H, int W, int cg, int relu_gate) {
+  const int OH = H / 2, OW = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % OW);
+  t /= OW;
+  const int h = (int)(t % OH);
+  const int b = (int)(t / OH);
+  const size_t C = (size_t)cg * 8;
+  const size_t off = (((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8;
+  float v[4][8], g[8], o[4][8];
+  ld8(x + off, v[0]);
+  ld8(x + off + C, v[1]);
+  ld8(x + off + (size_t)W * C, v[2]);
+  ld8(x + off + (size_t)W * C + C, v[3]);
+  ld8(gy + idx * 8, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int best = 0;
+    float m = v[0][j];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (v[k][j] > m) {
+        m = v[k][j];
+        best = k;
+      }
+    const float gv = (relu_gate && !(m > 0.f)) ? 0.f : g[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? gv : 0.f;
+  }
+  st8(gx + off, o[0]);
+  st8(gx + off + C, o[1]);
+  st8(gx + off + (size_t)W * C, o[2]);
+  st8(gx + off + (size_t)W * C + C, o[3]);
+}
+
+// torch adaptive_avg_pool2d windows: [floor(i*H/OH), ceil((i+1)*H/OH))
+__device__ __forceinline__ void adaptive_win(int i, int in, int out, int* s, int* e) {
+  *s = (i * in) / out;
+  *e = ((i + 1) * in + out - 1) / out;
+}
+__global__ void adaptive_avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int OH,
+                                            int OW, int cg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int ow = (int)(t % OW);
+  t /= OW;
+  const int oh = (int)(t % OH);
+  const int b = (int)(t / OH);
+  int hs, he, ws, we;
+  adaptive_win(oh, H, OH, &hs, &he);
+  adaptive_win(ow, W, OW, &ws, &we);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
+  for (int h = hs; h < he; ++h)
+    for (int w = ws; w < we; ++w) {
+      ld8(x + ((((size_t)b * H + h) * W + w) * cg + c) * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+  const float inv = 1.f / (float)((he - hs) * (we - ws));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= inv;
+  st8(y + idx * 8, acc);
+}
+__global__ void adaptive_avgpool_bwd_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ residual,
+                                            bf16* __restrict__ gx, int B, int H, int W, int OH, int OW, int cg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % W);
+  t /= W;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
+  for (int oh = 0; oh < OH; ++oh) {
+    int hs, he;
+    adaptive_win(oh, H, OH, &hs, &he);
+    if (h < hs || h >= he) continue;
+    for (int ow = 0; ow < OW; ++ow) {
+      int ws, we;
+      adaptive_win(ow, W, OW, &ws, &we);
+      if (w < ws || w >= we) continue;
+      const float inv = 1.f / (float)((he - hs) * (we - ws));
+      ld8(gy + ((((size_t)b * OH + oh) * OW + ow) * cg + c) * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j] * inv;
+    }
+  }
+  if (residual != nullptr) {
+    ld8(residual + idx * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += a[j];
+  }
+  st8(gx + idx * 8, acc);
+}
+
+// feat[b][c] = mean_p lrelu(x[b,p,c])  (models.py:125-127); one block per image, threads over channels
+__global__ void global_avgpool_lrelu_fwd_kernel(const bf16* __restrict__ x, float slope, float* __restrict__ out, int P,
+                                                int C) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc += lrelu_f(__bfloat162float(x[((size_t)b * P + p) * C + c]), slope);
+    out[(size_t)b * C + c] = acc / (float)P;
+  }
+}
+__global__ void global_avgpool_lrelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gfeat, float slope,
+                                                bf16* __restrict__ gx, int P, int C) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < P * C; i += blockDim.x) {
+    const int c = i % C;
+    const float xv = __bfloat162float(x[(size_t)b * P * C + i]);
+    const float g = gfeat[(size_t)b * C + c] / (float)P;
+    gx[(size_t)b * P * C + i] = __float2bfloat16(xv > 0.f ? g : g * slope);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = gamma * t + x   and its backward  (SelfAttention tail, models.py:274)
+// ---------------------------------------------------------------------------------------------
+__global__ void gamma_residual_fwd_kernel(const bf16* __restrict__ t, const bf16* __restrict__ x,
+                                          const float* __restrict__ gamma, bf16* __restrict__ out, long long n8) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const float g = __ldg(gamma);
+  float a[8], b[8];
+  ld8(t + idx * 8, a);
+  ld8(x + idx * 8, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = g * a[j] + b[j];
+  st8(out + idx * 8, a);
+}
+// gt = gamma * g ; dgamma += sum(g * t)
+__global__ void gamma_residual_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ t,
+                                          const float* __restrict__ gamma, bf16* __restrict__ gt,
+                                          float* __restrict__ dgamma, long long n8) {
+  const float gm = __ldg(gamma);
+  float acc = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    ld8(g + idx * 8, a);
+    ld8(t + idx * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc += a[j] * b[j];
+      a[j] *= gm;
+    }
+    st8(gt + idx * 8, a);
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dgamma, v);
+  }
+}
+
+// out_i[c] += sum_rows g[row][c]   (bias gradients; up to three identical destinations)
+__global__ void colsum_kernel(const bf16* __restrict__ g, long long rows, int cg, float* __restrict__ o0,
+                              float* __restrict__ o1, float* __restrict__ o2) {
+  extern __shared__ float sh[];  // [prows][cg*8]
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
+  if (pr < prows)
+    for (long long r = (long long)blockIdx.x * prows + pr; r < rows; r += (long long)gridDim.x * prows) {
+      ld8(g + (r * cg + c) * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+  if (pr < prows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[(pr * cg + c) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  const int C = cg * 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < prows; ++r) s += sh[r * C + i];
+    atomicAdd(o0 + i, s);
+    if (o1 != nullptr) atomicAdd(o1 + i, s);
+    if (o2 != nullptr) atomicAdd(o2 + i, s);
+  }
+}
+
+// dw[(t*cin_stride + ci_row)*Cout + co] += sum_{b,h,w} mask[b,h+dy,w+dx] * g[b,h,w,co]
+// (weight gradient of the mask channel of `cat(feature*mask, mask)`, models.py:94,336)
+__global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16* __restrict__ g, int B, int H, int W,
+                                     int cg, float* __restrict__ dw, int cin_stride, int ci_row) {
+  extern __shared__ float sh[];  // [prows][9][C]
+  const int C = cg * 8;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long npix = (long long)B * H * W;
+  if (pr < prows)
+    for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
+      const int w = (int)(p % W);
+      const int h = (int)((p / W) % H);
+      const long long bbase = p - (long long)h * W - w;
+      float mk[9];
+      bool any = false;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+        mk[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(mask + bbase + (long long)hh * W + ww) : 0.f;
+        any = any || (mk[t] != 0.f);
+      }
+      if (!any) continue;
+      float a[8];
+      ld8(g + (p * cg + c) * 8, a);
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] += mk[t] * a[j];
+    }
+  if (pr < prows) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh[(pr * 9 + t) * C + c * 8 + j] = acc[t][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < prows; ++r) s += sh[r * 9 * C + i];
+    const int t = i / C, co = i % C;
+    if (s != 0.f) atomicAdd(dw + ((size_t)t * cin_stride + ci_row) * C + co, s);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) dst[idx] = __float2bfloat16(src[idx]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generator tail: img = tanh(conv1x1(a; W/sigma) + b), C -> 3 channels, NCHW f32 out  (models.py:58-61,99)
+// ---------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void conv1x1_tanh_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                        const float* __restrict__ sigma, const float* __restrict__ bias,
+                                        float* __restrict__ img, int HW, int C, long long npix) {
+  extern __shared__ float ws[];  // [CO][C]
+  const float inv = 1.f / __ldg(sigma);
+  for (int i = threadIdx.x; i < CO * C; i += blockDim.x) ws[i] = w[i] * inv;
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = bias[o];
+  for (int k = 0; k < C; k += 8) {
+    float v[8];
+    ld8(a + p * C + k, v);
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o] += v[j] * ws[o * C + k + j];
+  }
+  const long long b = p / HW, q = p % HW;
+#pragma unroll
+  for (int o = 0; o < CO; ++o) img[((size_t)b * CO + o) * HW + q] = tanhf(acc[o]);
+}
+// gh[p][k] = (sum_o gpre[o] W[o][k]/sigma) * lrelu'(a[p][k]);  dW_sn[o][k] += sum_p gpre[o] a[p][k];  db[o] += sum_p gpre[o]
+template <int CO>
+__global__ void conv1x1_tanh_bwd_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
+                                        const bf16* __restrict__ a, const float* __restrict__ w,
+                                        const float* __restrict__ sigma, float slope, bf16* __restrict__ gh,
+                                        float* __restrict__ dw, float* __restrict__ db, int HW, int C, long long npix) {
+  extern __shared__ float sh[];  // ws[CO][C] then red[prows][CO][C] then redb[prows][CO]
+  const int cg = C / 8;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  float* ws = sh;
+  float* red = sh + CO * C;
+  float* redb = red + prows * CO * C;
+  const float inv = 1.f / __ldg(sigma);
+  for (int i = threadIdx.x; i < CO * C; i += blockDim.x) ws[i] = w[i] * inv;
+  __syncthreads();
+  float accw[CO][8], accb[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    accb[o] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accw[o][j] = 0.f;
+  }
+  if (pr < prows)
+    for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
+      const long long b = p / HW, q = p % HW;
+      float gp[CO];
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float y = __ldg(img + ((size_t)b * CO + o) * HW + q);
+        gp[o] = __ldg(gimg + ((size_t)b * CO + o) * HW + q) * (1.f - y * y);
+      }
+      float v[8], o8[8];
+      ld8(a + p * C + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          s += gp[o] * ws[o * C + c * 8 + j];
+          accw[o][j] += gp[o] * v[j];
+        }
+        o8[j] = v[j] > 0.f ? s : s * slope;
+      }
+      st8(gh + p * C + c * 8, o8);
+      if (c == 0) {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) accb[o] += gp[o];
+      }
+    }
+  if (pr < prows) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(pr * CO + o) * C + c * 8 + j] = accw[o][j];
+      if (c == 0) redb[pr * CO + o] = accb[o];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CO * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < prows; ++r) s += red[r * CO * C + i];
+    atomicAdd(dw + i, s);
+  }
+  if (threadIdx.x < CO) {
+    float s = 0.f;
+    for (int r = 0; r < prows; ++r) s += redb[r * CO + threadIdx.x];
+    atomicAdd(db + threadIdx.x, s);
+  }
+}
+
+}  // namespace
+
+#define SPYR_C8(C) SPYR_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channel count %d must be a multiple of 8", __func__, (int)(C))
+
+extern "C" int spyr_im2col3x3(const float* img, int B, int H, int W, const float* mean3, const float* invstd3, void* out,
+                              void* stream) {
+  SPYR_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "im2col3x3: bad arguments");
+  const long long n = (long long)B * H * W;
+  im2col3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(img, B, H, W, mean3, invstd3, (bf16*)out);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float* invstd3, float* gimg, int accumulate,
+                              void* stream) {
+  SPYR_REQUIRE(gcol && gimg && B > 0, "col2im3x3: bad arguments");
+  const long long n = (long long)B * H * W;
+  col2im3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)gcol, B, H, W, invstd3, gimg,
+                                                                       accumulate);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void* out, void* stream) {
+  SPYR_REQUIRE(img && out && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8: bad arguments");
+  const long long n = (long long)B * (H / 2) * (W / 2);
+  img_avgpool_pad8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, (bf16*)out);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_img_avgpool_pad8_bwd(const void* g8, int B, int H, int W, float* gimg, int accumulate, void* stream) {
+  SPYR_REQUIRE(g8 && gimg && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8_bwd: bad arguments");
+  const long long n = (long long)B * H * W;
+  img_avgpool_pad8_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g8, B, H, W, gimg,
+                                                                                  accumulate);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_nchw_to_nhwc(const float* src, const float* mask, void* dst, int B, int C, int HW, void* stream) {
+  SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, (bf16*)dst, C, HW);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_nhwc_to_nchw(const void* src, float* dst, int B, int C, int HW, void* stream) {
+  SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, HW);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream) {
+  SPYR_C8(C);
+  maskgate_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)f, mask, (bf16*)out, npix,
+                                                                                   C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_raw, void* y_act, float slope, int B, int H,
+                                 int W, int C, void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2_fwd: odd size");
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  avgpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)residual,
+                                                                          (bf16*)y_raw, (bf16*)y_act, slope, B, H, W, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_avgpool2_bwd(const void* g_lo, void* g_hi, int B, int H, int W, int C, void* stream) {
+  SPYR_C8(C);
+  const long long n = (long long)B * H * W * (C / 8);
+  avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g_lo, (bf16*)g_hi, B, H, W, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: odd size");
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B, int H, int W, int C, int relu_gate,
+                                 void* stream) {
+  SPYR_C8(C);
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gy, (bf16*)gx, B, H,
+                                                                          W, C / 8, relu_gate);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_adaptive_avgpool_fwd(const void* x, void* y, int B, int H, int W, int OH, int OW, int C, void* stream) {
+  SPYR_C8(C);
+  const long long n = (long long)B * OH * OW * (C / 8);
+  adaptive_avgpool_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, OH, OW,
+                                                                                  C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_adaptive_avgpool_bwd(const void* gy, const void* residual, void* gx, int B, int H, int W, int OH,
+                                         int OW, int C, void* stream) {
+  SPYR_C8(C);
+  const long long n = (long long)B * H * W * (C / 8);
+  adaptive_avgpool_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)gy, (const bf16*)residual, (bf16*)gx, B, H, W, OH, OW, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_global_avgpool_lrelu_fwd(const void* x, float slope, float* out, int B, int P, int C, void* stream) {
+  global_avgpool_lrelu_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, slope, out, P, C);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, float slope, void* gx, int B, int P, int C,
+                                             void* stream) {
+  global_avgpool_lrelu_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gfeat, slope, (bf16*)gx, P, C);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, long long n,
+                                       void* stream) {
+  SPYR_REQUIRE(n % 8 == 0, "gamma_residual_fwd: n must be a multiple of 8");
+  gamma_residual_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)t, (const bf16*)x, gamma,
+                                                                                    (bf16*)out, n / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_gamma_residual_bwd(const void* g, const void* t, const float* gamma, void* gt, float* dgamma,
+                                       long long n, void* stream) {
+  SPYR_REQUIRE(n % 8 == 0, "gamma_residual_bwd: n must be a multiple of 8");
+  int grid = grid_for(n / 8, 256);
+  if (grid > 592) grid = 592;
+  gamma_residual_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)g, (const bf16*)t, gamma, (bf16*)gt,
+                                                                    dgamma, n / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* stream) {
+  SPYR_C8(C);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 256, "colsum: C=%d too large", C);
+  const int prows = 256 / cg;
+  const int threads = prows * cg;
+  long long want = (rows + prows * 8 - 1) / (prows * 8);
+  int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
+  colsum_kernel<<<grid, threads, (size_t)prows * C * 4, (cudaStream_t)stream>>>((const bf16*)g, rows, cg, out0, out1, out2);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride,
+                                  int ci_row, void* stream) {
+  SPYR_C8(C);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 128, "stencil_wgrad: C=%d too large", C);
+  int prows = 128 / cg;
+  if (prows > 4) prows = 4;
+  const int threads = prows * cg;
+  const size_t smem = (size_t)prows * 9 * C * 4;
+  static bool configured = false;
+  if (!configured) {
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  const long long npix = (long long)B * H * W;
+  long long want = (npix + prows * 16 - 1) / (prows * 16);
+  int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
+  stencil_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mask, (const bf16*)g, B, H, W, cg, dw, cin_stride,
+                                                                      ci_row);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float* sigma, const float* bias, float* img,
+                                     int B, int HW, int C, int Cout, void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(Cout == 3 || Cout == 1, "conv1x1_tanh_fwd: out_channels must be 1 or 3 (got %d)", Cout);
+  const long long npix = (long long)B * HW;
+  const size_t smem = (size_t)Cout * C * 4;
+  if (Cout == 3)
+    conv1x1_tanh_fwd_kernel<3><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>((const bf16*)a, w, sigma, bias, img,
+                                                                                         HW, C, npix);
+  else
+    conv1x1_tanh_fwd_kernel<1><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>((const bf16*)a, w, sigma, bias, img,
+                                                                                         HW, C, npix);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, const float* w, const float* sigma,
+                                     float slope, void* gh, float* dw, float* db, int B, int HW, int C, int Cout,
+                                     void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(Cout == 3 || Cout == 1, "conv1x1_tanh_bwd: out_channels must be 1 or 3 (got %d)", Cout);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 64, "conv1x1_tanh_bwd: C=%d too large", C);
+  const int prows = 256 / cg;
+  const int threads = prows * cg;
+  const long long npix = (long long)B * HW;
+  const size_t smem = ((size_t)Cout * C + (size_t)prows * Cout * C + (size_t)prows * Cout) * 4;
+  SPYR_REQUIRE(smem <= 48 * 1024, "conv1x1_tanh_bwd: smem %zu too large", smem);
+  long long want = (npix + prows * 16 - 1) / (prows * 16);
+  int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  if (Cout == 3)
+    conv1x1_tanh_bwd_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, (const bf16*)a, w, sigma, slope,
+                                                                              (bf16*)gh, dw, db, HW, C, npix);
+  else
+    conv1x1_tanh_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, (const bf16*)a, w, sigma, slope,
+                                                                              (bf16*)gh, dw, db, HW, C, npix);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}

@@ -219,6 +219,127 @@ static int test_wgrad(int B, int H, int W, int Cin, int Cout, int ks, int lbo, i
   return ok ? 0 : 1;
 }
 
+// input-gradient mode: same fprop pack w[t][co][ci], read MN-major with flipped taps
+static int test_dgrad(int B, int H, int W, int Cin_f, int Cout_f, int ks, bool f32) {
+  const int taps = ks * ks, pad = ks / 2;
+  std::vector<float> g((size_t)B * H * W * Cout_f), w((size_t)taps * Cout_f * Cin_f);
+  for (auto& v : g) v = bf16_round(frand());
+  for (auto& v : w) v = bf16_round(frand() * 0.05f);
+  std::vector<float> ref((size_t)B * H * W * Cin_f, 0.f);
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int x = 0; x < W; ++x)
+        for (int t = 0; t < taps; ++t) {
+          // forward: y[h][x] += in[h+dy][x+dx] * w[t]  =>  gin[h+dy][x+dx] += g[h][x] * w[t]
+          const int hh = h + t / ks - pad, xx = x + t % ks - pad;
+          if (hh < 0 || hh >= H || xx < 0 || xx >= W) continue;
+          const float* gp = &g[(((size_t)b * H + h) * W + x) * Cout_f];
+          float* rp = &ref[(((size_t)b * H + hh) * W + xx) * Cin_f];
+          for (int co = 0; co < Cout_f; ++co) {
+            const float gv = gp[co];
+            const float* wp = &w[((size_t)t * Cout_f + co) * Cin_f];
+            for (int ci = 0; ci < Cin_f; ++ci) rp[ci] += gv * wp[ci];
+          }
+        }
+  Dev dg, dw, dy;
+  auto gb = to_bf16(g); auto wb = to_bf16(w);
+  dg.alloc(gb.size() * 2); dw.alloc(wb.size() * 2);
+  CK(cudaMemcpy(dg.p, gb.data(), gb.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  spyr_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.H = H; d.W = W; d.Cout = Cin_f; d.nsrc = 1;
+  d.src[0].x = dg.p; d.src[0].w = dw.p; d.src[0].cin = Cout_f; d.src[0].ksize = ks; d.src[0].w_mn_major = 1;
+  const size_t ny = ref.size();
+  dy.alloc(ny * (f32 ? 4 : 2));
+  if (f32) { d.y_f32 = (float*)dy.p; d.f32_store = 1; } else d.y_raw = dy.p;
+  int rc = spyr_conv2d_fprop(&d, 0);
+  if (rc) { printf("  dgrad rc=%d: %s\n", rc, spyr_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  dgrad kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(ny);
+  if (f32) CK(cudaMemcpy(got.data(), dy.p, ny * 4, cudaMemcpyDeviceToHost));
+  else {
+    std::vector<__nv_bfloat16> ob(ny);
+    CK(cudaMemcpy(ob.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ny; ++i) got[i] = __bfloat162float(ob[i]);
+  }
+  const double err = rel_l2(got, ref);
+  const bool ok = err < (f32 ? 1e-5 : 5e-3);
+  printf("%s dgrad B=%d %dx%d Cin_f=%d Cout_f=%d k=%d f32=%d relL2=%.3e\n", ok ? "PASS" : "FAIL", B, H, W, Cin_f, Cout_f,
+         ks, (int)f32, err);
+  return ok ? 0 : 1;
+}
+
+// per-image weights (batched GEMM): mn=0: y[b,p,n] = sum_k x[b,p,k] w[b][n][k];  mn=1: w[b][k][n]
+static int test_per_image(int B, int H, int W, int K, int N, int mn) {
+  std::vector<float> x((size_t)B * H * W * K), w((size_t)B * N * K);
+  for (auto& v : x) v = bf16_round(frand());
+  for (auto& v : w) v = bf16_round(frand() * 0.1f);
+  std::vector<float> ref((size_t)B * H * W * N, 0.f);
+  for (int b = 0; b < B; ++b)
+    for (int p = 0; p < H * W; ++p)
+      for (int n = 0; n < N; ++n) {
+        double acc = 0;
+        for (int k = 0; k < K; ++k)
+          acc += (double)x[((size_t)b * H * W + p) * K + k] * (mn ? w[((size_t)b * K + k) * N + n] : w[((size_t)b * N + n) * K + k]);
+        ref[((size_t)b * H * W + p) * N + n] = (float)acc;
+      }
+  Dev dx, dw, dy;
+  auto xb = to_bf16(x); auto wb = to_bf16(w);
+  dx.alloc(xb.size() * 2); dw.alloc(wb.size() * 2); dy.alloc(ref.size() * 4);
+  CK(cudaMemcpy(dx.p, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  spyr_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.H = H; d.W = W; d.Cout = N; d.nsrc = 1;
+  d.src[0].x = dx.p; d.src[0].w = dw.p; d.src[0].cin = K; d.src[0].ksize = 1; d.src[0].w_mn_major = mn;
+  d.src[0].w_per_image = 1;
+  d.y_f32 = (float*)dy.p; d.f32_store = 1;
+  int rc = spyr_conv2d_fprop(&d, 0);
+  if (rc) { printf("  per_image rc=%d: %s\n", rc, spyr_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  per_image kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(ref.size());
+  CK(cudaMemcpy(got.data(), dy.p, ref.size() * 4, cudaMemcpyDeviceToHost));
+  const double err = rel_l2(got, ref);
+  const bool ok = err < 1e-5;
+  printf("%s per_image B=%d %dx%d K=%d N=%d mn=%d relL2=%.3e\n", ok ? "PASS" : "FAIL", B, H, W, K, N, mn, err);
+  return ok ? 0 : 1;
+}
+
+static int test_wgrad_per_image(int B, int H, int W, int Cin, int Cout) {
+  const size_t nx = (size_t)B * H * W * Cin, ny = (size_t)B * H * W * Cout;
+  std::vector<float> x(nx), dy(ny);
+  for (auto& v : x) v = bf16_round(frand());
+  for (auto& v : dy) v = bf16_round(frand() * 0.1f);
+  std::vector<float> ref((size_t)B * Cin * Cout, 0.f);
+  for (int b = 0; b < B; ++b)
+    for (int p = 0; p < H * W; ++p)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+          ref[((size_t)b * Cin + ci) * Cout + co] += x[((size_t)b * H * W + p) * Cin + ci] * dy[((size_t)b * H * W + p) * Cout + co];
+  Dev dx, ddy, ddw;
+  auto xb = to_bf16(x); auto yb = to_bf16(dy);
+  dx.alloc(nx * 2); ddy.alloc(ny * 2); ddw.alloc(ref.size() * 4);
+  CK(cudaMemcpy(dx.p, xb.data(), nx * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ddy.p, yb.data(), ny * 2, cudaMemcpyHostToDevice));
+  spyr_wgrad_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = 1;
+  d.x = dx.p; d.dy = ddy.p; d.dw = (float*)ddw.p; d.per_image = 1;
+  int rc = spyr_conv2d_wgrad(&d, 0);
+  if (rc) { printf("  wgrad_pi rc=%d: %s\n", rc, spyr_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  wgrad_pi kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(ref.size());
+  CK(cudaMemcpy(got.data(), ddw.p, ref.size() * 4, cudaMemcpyDeviceToHost));
+  const double err = rel_l2(got, ref);
+  const bool ok = err < 1e-4;
+  printf("%s wgrad_per_image B=%d %dx%d Cin=%d Cout=%d relL2=%.3e\n", ok ? "PASS" : "FAIL", B, H, W, Cin, Cout, err);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int fails = 0;
   const char* mode = argc > 1 ? argv[1] : "all";
@@ -244,6 +365,23 @@ int main(int argc, char** argv) {
     fails += test_wgrad(2, 32, 32, 256, 32, 1, 0, 0, 0);
     fails += test_wgrad(2, 64, 64, 64, 64, 3, 0, 0, 0);
     fails += test_wgrad(20, 1, 1, 512, 128, 1, 0, 0, 0);
+  }
+  if (!strcmp(mode, "all") || !strcmp(mode, "dgrad")) {
+    fails += test_dgrad(2, 16, 16, 64, 64, 3, false);
+    fails += test_dgrad(2, 16, 16, 128, 256, 3, true);
+    fails += test_dgrad(3, 8, 8, 256, 128, 3, false);
+    fails += test_dgrad(2, 16, 16, 64, 128, 1, true);
+    fails += test_dgrad(2, 32, 32, 32, 64, 1, true);   // im2col'd first layer: 32 output channels
+    fails += test_dgrad(5, 4, 4, 512, 768, 3, true);
+    fails += test_dgrad(2, 16, 16, 8, 64, 1, true);    // padded 3-channel skip path
+    fails += test_per_image(3, 32, 32, 32, 256, 0);    // S = Q K^T
+    fails += test_per_image(3, 32, 32, 256, 128, 1);   // O = P V
+    fails += test_per_image(3, 32, 32, 128, 256, 0);   // dP = dO V^T
+    fails += test_per_image(3, 32, 32, 256, 32, 1);    // dQ = dS K
+    fails += test_per_image(2, 16, 16, 64, 16, 1);     // channel_factor 2 head dims
+    fails += test_wgrad_per_image(3, 32, 32, 256, 32);  // dK
+    fails += test_wgrad_per_image(3, 32, 32, 256, 128); // dV
+    fails += test_wgrad_per_image(2, 16, 16, 64, 16);
   }
   printf("native conv tests: %d failure(s)\n", fails);
   return fails ? 1 : 0;
