@@ -56,6 +56,8 @@ typedef struct {
   int nsrc;
   spyr_conv_src src[3];
   const float* bias;          /* [Cout] or NULL */
+  const float* bias2;         /* further bias vectors added in the epilogue (fused residual branches), or NULL */
+  const float* bias3;
   const float* stencil_mask;  /* f32 [B,H,W] or NULL: extra 1-channel 3x3 conv input (models.py:94 `cat(.., mask)`) */
   const float* stencil_w;     /* f32 [10][Cout]: 9 taps + row 9 = sum over taps */
   const void* dmask;          /* NHWC bf16 [B,H,W,Cout] or NULL */
@@ -82,6 +84,9 @@ typedef struct {
   const void* x;   /* NHWC bf16 [B,H,W,Cin]  */
   const void* dy;  /* NHWC bf16 [B,H,W,Cout] */
   float* dw;       /* f32 [taps][Cin][Cout]  */
+  int cin_stride;  /* 0 = Cin; else row stride (in input channels) of dw: element (tap, ci, co) lives at
+                      dw[(tap*cin_stride + ci)*Cout + co] -- lets the mask channel of `cat(feature*mask, mask)` share the
+                      buffer (models.py:94) */
   int splits;      /* 0 = auto */
   int stages;      /* 0 = auto */
   int per_image;   /* 1: one dw slice per image, dw is f32 [B][taps][Cin][Cout] (attention dK/dV, models.py:266-268) */
@@ -90,6 +95,159 @@ typedef struct {
 } spyr_wgrad_desc;
 
 int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image <-> first-layer operand.  The 3-channel 3x3 convolutions (VGG features.0, models.py:201; Discriminator
+ * layers.0.main_block.0, models.py:393) run as a 1x1 tensor-core conv over 32-wide im2col rows
+ * (k = tap*3 + c, columns 27..31 zero).  `mean3/invstd3` (may be NULL) fold kornia.normalize (models.py:195-197).
+ * Images are NCHW FP32 (data.py:76-90).
+ * ------------------------------------------------------------------------------------------------ */
+int spyr_im2col3x3(const float* img, int B, int H, int W, const float* mean3, const float* invstd3, void* out, void* stream);
+int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float* invstd3, float* gimg, int accumulate, void* stream);
+/* AvgPool2d(2) of the image for the input block's skip conv (models.py:417): (B,3,H,W) f32 -> (B,H/2,W/2,8) bf16 */
+int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void* out, void* stream);
+int spyr_img_avgpool_pad8_bwd(const void* g8, int B, int H, int W, float* gimg, int accumulate, void* stream);
+/* API-boundary layout conversion; `mask` (f32 [B,HW], may be NULL) gates the feature (models.py:94) */
+int spyr_nchw_to_nhwc(const float* src, const float* mask, float slope, void* dst, int B, int C, int HW, void* stream);
+/* gate_x (f32 NCHW, may be NULL): dst *= (gate_x > 0 ? 1 : slope) -- backward of the LeakyReLU at models.py:33 */
+int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slope, float* dst, int B, int C, int HW, void* stream);
+int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream);
+
+/* pooling (NHWC bf16; H, W are the HIGH-resolution dims everywhere) */
+int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_raw, void* y_act, float slope, int B, int H, int W, int C,
+                      void* stream); /* models.py:406,415-418,451,465; residual is added after pooling */
+int spyr_avgpool2_bwd(const void* g_lo, void* g_hi, int B, int H, int W, int C, void* stream);
+int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream); /* models.py:203,245 */
+int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B, int H, int W, int C, int relu_gate, int accumulate,
+                      void* stream);
+int spyr_adaptive_avgpool_fwd(const void* x, void* y, int B, int H, int W, int OH, int OW, int C, void* stream); /* :206 */
+int spyr_adaptive_avgpool_bwd(const void* gy, const void* residual, void* gx, int B, int H, int W, int OH, int OW, int C,
+                              void* stream);
+int spyr_global_avgpool_lrelu_fwd(const void* x, float slope, float* out, int B, int P, int C, void* stream); /* :125-127 */
+int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, float slope, void* gx, int B, int P, int C, void* stream);
+
+/* out = gamma*t + x (models.py:274) and backward (gt = gamma*g, dgamma += <g,t>) */
+int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, void* out_act, float slope,
+                            long long n, void* stream);
+int spyr_gamma_residual_bwd(const void* g, const void* t, const float* gamma, void* gt, float* dgamma, long long n, void* stream);
+/* bias gradients: out_i[c] += sum_rows g[row][c] (out1/out2 may be NULL) */
+int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* stream);
+/* weight gradient of the mask channel of cat(feature*mask, mask): dw[(t*cin_stride+ci_row)*C + co] += ... */
+int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride, int ci_row,
+                       void* stream);
+int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* epilogue of the split-K FC layers (VGG classifier, models.py:210-213) and of their input-gradients:
+ * v = acc[b][n] + bias[n] + add[b][n]; mode 1: v = relu(v); mode 2: v *= (gate[b][n] > 0); any pointer may be NULL */
+int spyr_vec_epilogue(const float* acc, const float* bias, const float* add, const float* gate, int mode, float* out_f32,
+                      void* out_bf16, int ld_bf16 /* row stride of out_bf16, >= N */, int B, int N, void* stream);
+/* generator tail: img = tanh(conv1x1(a; W/sigma) + b) -> NCHW f32 (models.py:58-61,99) and its backward, which emits
+ * the gradient w.r.t. the PRE-LeakyReLU input of the 1x1 conv (gate from a), dW (w.r.t. W/sigma) and db */
+int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float* sigma, const float* bias, float* img, int B, int HW,
+                          int C, int Cout, void* stream);
+int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, const float* w, const float* sigma, float slope,
+                          void* gh, float* dw, float* db, int B, int HW, int C, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (Conditional) batch norm, train-mode statistics, fused with LeakyReLU and bilinear x2 (align_corners=True).
+ * models.py:491-506 (ConditionalBatchNorm), :51-54 (final block), :295-310 (generator block).
+ * Affine convention: scale = scale_ptr[row*row_stride + c], shift = shift_ptr[row*row_stride + c], row = cls[b] or 0.
+ * mode 0: a = lrelu(aff(x));  mode 1: a = up2(lrelu(aff(x))), xu = up2(x);  mode 2: a = lrelu(aff(up2(x))).
+ * ------------------------------------------------------------------------------------------------ */
+int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums /* [2C] */, void* stream);
+int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float* mean_rstd /* [2C] */, int training,
+                     void* stream);
+int spyr_bn_act(const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr, int row_stride,
+                const int* cls, float slope, int mode, void* out_a, void* out_xu, int B, int H, int W, int C, void* stream);
+int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr,
+                       int row_stride, const int* cls, float slope, int mode, void* gy_out, float* S /* [B][2][C] */, int B,
+                       int H, int W, int C, void* stream);
+int spyr_bn_bwd_finalize(const float* S, int B, int C, float count, const float* scale_ptr, int row_stride, const int* cls,
+                         float* M /* [2C] */, float* d_scale, float* d_shift, void* stream);
+int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mean_rstd, const float* scale_ptr, int row_stride,
+                      const int* cls, const float* M, const void* residual, void* gx, int B, int H, int W, int C, int x_up2,
+                      void* stream); /* x_up2: gy/gx at 2H x 2W, xhat from up2(x); H, W are x's dims */
+int spyr_up2_bwd(const void* g_hi, void* g_lo, int B, int H, int W, int C, void* stream); /* H, W = LOW-res dims */
+int spyr_argmax_rows(const void* onehot, int is_int64, int B, int n, int* out, void* stream); /* models.py:151,501 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral normalisation of every layer of a model in one batched pass (torch spectral_norm.py:92-114).
+ * The table is static per model (pointers to weight_orig / weight_u / weight_v); per-forward outputs go to
+ * caller-provided arenas at the offsets recorded in the table.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* w;        /* weight_orig viewed as (rows, cols); conv element (co, ci, t) at co*cols + ci*taps + t */
+  float* u;              /* weight_u [rows], updated in place in training mode */
+  float* v;              /* weight_v [cols] */
+  int rows, cols, taps, cin; /* cols = cin * taps */
+  int pack_cin;          /* >0: emit bf16 packed[t][rows][pack_cin] at pack_off; 0: FP32 consumers only need sigma */
+  int pack_mode;         /* 0: as above.  1: im2col rows packed[rows][pack_cin], k = t*cin + ci, zero padded (3-channel
+                            first layers, models.py:393,403) */
+  long long pack_off;    /* element offset into the bf16 arena */
+  long long stencil_off; /* >=0: cin == pack_cin + 1, emit f32 stencil[10][rows] for channel pack_cin; else -1 */
+  long long gw_off;      /* backward: float offset of G = dL/d(W/sigma) in gw_arena, or -1 (no gradient this pass) */
+  int gw_layout;         /* 0: same layout as w;  1: [tap][cin][rows] (spyr_conv2d_wgrad order) */
+  long long grad_off;    /* backward: float offset of dL/dweight_orig in grad_arena (layout of w) */
+  /* filled by spyr_sn_plan: */
+  int index, tile0_wtu, tile0_wv, tile0_pack, tile0_bwd;
+  long long scratch_off, saved_off; /* saved arena per layer: sigma, u[rows], v[cols] (the clones torch keeps) */
+} spyr_sn_layer;
+typedef struct {
+  int tiles_wtu, tiles_wv, tiles_pack, tiles_bwd;
+  long long scratch_floats, saved_floats;
+} spyr_sn_plan_out;
+int spyr_sn_plan(spyr_sn_layer* host_tab, int n, spyr_sn_plan_out* out); /* host only; fills the planning fields */
+int spyr_sn_forward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, int training, float eps,
+                    float* scratch, void* packed, float* stencil, float* saved, void* stream);
+int spyr_sn_backward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, const float* gw_arena,
+                     const float* saved, float* dots /* [n] */, float* grad_arena, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small-batch FP32 linear layers (models.py:28-31,356,360,128,132): y = lrelu_out((f(x) W^T)/sigma + b + y_add),
+ * f(x) = lrelu_in(x * xmask).  slopes of 1 disable the activations; sigma/bias/xmask/y_add may be NULL.
+ * ------------------------------------------------------------------------------------------------ */
+int spyr_linear_fwd(const float* x, const float* xmask, float in_slope, const float* w, const float* sigma,
+                    const float* bias, const float* y_add, float out_slope, float* y, int B, int K, int O, void* stream);
+int spyr_linear_bwd_x(const float* gy, const float* y, float out_slope, const float* w, const float* sigma, const float* x,
+                      float in_slope, float* gx, int accumulate, int B, int K, int O, void* stream);
+int spyr_linear_bwd_w(const float* gy, const float* y, float out_slope, const float* x, const float* xmask, float in_slope,
+                      float* gw, float* gb, int B, int K, int O, void* stream);
+/* Discriminator output (B,B,E): out[i][j][k] = cls[j] + feat[j][k]*emb_w[idx[i]][k]/sigma (models.py:151-155) */
+int spyr_dhead_out_fwd(const float* cls, const float* feat, const float* emb_w, const float* sigma, const int* idx,
+                       float* out, int B, int E, void* stream);
+int spyr_dhead_out_bwd(const float* g, const float* feat, const float* emb_w, const float* sigma, const int* idx,
+                       float* g_cls, float* g_feat, float* g_embw, int B, int E, void* stream);
+
+/* attention-map softmax over keys (models.py:266) and its backward */
+int spyr_softmax_rows_fwd(const float* s, void* p, long long rows, int n, void* stream);
+int spyr_softmax_rows_bwd(const void* p, const float* dp, void* ds, long long rows, int n, void* stream);
+
+/* losses (lossfunction.py) */
+int spyr_lsgan_fwd(const float* p, long long n, float target, float* out, void* stream);           /* :137,:164 */
+int spyr_lsgan_bwd(const float* p, long long n, float target, const float* gout, float* gp, void* stream);
+int spyr_rec_level_fwd(const void* fr, const void* ff, const float* mask, int B, int H, int W, int C, float* loss,
+                       void* stream);                                                               /* :45-49,67 (loss +=) */
+int spyr_rec_level_bwd(const void* fr, const void* ff, const float* mask, int B, int H, int W, int C, const float* gout,
+                       void* gff, void* stream);
+int spyr_rec_vec_fwd(const float* fr, const float* ff, const float* mask, int B, int N, float* loss, void* stream); /* :57-59 */
+int spyr_rec_vec_bwd(const float* fr, const float* ff, const float* mask, int B, int N, const float* gout, float* gff,
+                     void* stream);
+int spyr_diversity_fwd(const float* img, long long img_half, const float* z, long long z_half, float* work /* [2] */,
+                       float* loss, void* stream);                                                  /* :102-110 */
+int spyr_diversity_bwd(const float* img, long long img_half, const float* work, const float* gout, float* gimg, void* stream);
+
+/* fused multi-tensor Adam (torch.optim.Adam defaults, main.py:64-65); the step counter lives on the device */
+#define SPYR_ADAM_MAX_TENSORS 48
+typedef struct {
+  int count;
+  float* p[SPYR_ADAM_MAX_TENSORS];
+  const float* g[SPYR_ADAM_MAX_TENSORS];
+  float* m[SPYR_ADAM_MAX_TENSORS];
+  float* v[SPYR_ADAM_MAX_TENSORS];
+  long long n[SPYR_ADAM_MAX_TENSORS];
+} spyr_adam_chunk;
+int spyr_adam_tick(int* step, void* stream);
+int spyr_adam_step(const spyr_adam_chunk* chunk, const int* step, float lr, float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,8 @@ struct FpropParams {
   int splits;
   uint32_t tmem_cols;
   const float* bias;
+  const float* bias2;
+  const float* bias3;
   const float* stencil_mask;
   const float* stencil_w;
   const bf16* dmask;
@@ -262,6 +264,14 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += __ldg(&p.bias[col + j]);
           }
+          if (p.bias2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += __ldg(&p.bias2[col + j]);
+          }
+          if (p.bias3 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += __ldg(&p.bias3[col + j]);
+          }
           if (mk_mode == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += __ldg(&p.stencil_w[9 * p.Cout + col + j]);
@@ -345,6 +355,7 @@ struct WgradParams {
   uint32_t tmem_cols;
   uint32_t lbo, sbo;
   int per_image;    // splits per image when > 0 (dw gets one slice per image)
+  int cin_stride;   // row stride of dw in input channels
   float* dw;
 };
 
@@ -480,7 +491,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         tmem_ld_wait();
         if (!valid) continue;
         const int col0 = n_off + c0;
-        float* dst = dw_out + ((size_t)tap * p.Cin + ci) * p.Cout + col0;
+        float* dst = dw_out + ((size_t)tap * p.cin_stride + ci) * p.Cout + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -595,6 +606,8 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   p.stages = stages;
   p.tmem_cols = pow2_cols(bn);
   p.bias = d->bias;
+  p.bias2 = d->bias2;
+  p.bias3 = d->bias3;
   p.stencil_mask = d->stencil_mask;
   p.stencil_w = d->stencil_w;
   p.dmask = (const bf16*)d->dmask;
@@ -668,6 +681,8 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
   p.lbo = d->dbg_lbo ? (uint32_t)d->dbg_lbo : (uint32_t)(KP * 128);
   p.sbo = d->dbg_sbo ? (uint32_t)d->dbg_sbo : 1024u;
   p.dw = d->dw;
+  p.cin_stride = d->cin_stride > 0 ? d->cin_stride : d->Cin;
+  SPYR_REQUIRE(!d->per_image || p.cin_stride == d->Cin, "conv2d_wgrad: per_image cannot use cin_stride");
 
   WgradMaps maps;
   {

@@ -135,8 +135,8 @@ __global__ void img_avgpool_pad8_bwd_kernel(const bf16* __restrict__ g8, int B, 
 // ---------------------------------------------------------------------------------------------
 // NCHW f32 <-> NHWC bf16 (API boundary only), optional per-pixel mask gate
 // ---------------------------------------------------------------------------------------------
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ mask, bf16* __restrict__ dst,
-                                    int C, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ mask, float slope,
+                                    bf16* __restrict__ dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -150,11 +150,12 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* 
     if (p < HW && c < C) {
       float v = tile[threadIdx.x][i];
       if (mask != nullptr) v *= mask[(size_t)b * HW + p];
-      dst[((size_t)b * HW + p) * C + c] = __float2bfloat16(v);
+      dst[((size_t)b * HW + p) * C + c] = __float2bfloat16(lrelu_f(v, slope));
     }
   }
 }
-__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, const float* __restrict__ gate_x, float slope,
+                                    float* __restrict__ dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -165,7 +166,12 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restr
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, p = p0 + threadIdx.x;
-    if (c < C && p < HW) dst[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][i];
+    if (c < C && p < HW) {
+      const size_t o = ((size_t)b * C + c) * HW + p;
+      float v = tile[threadIdx.x][i];
+      if (gate_x != nullptr && !(gate_x[o] > 0.f)) v *= slope;
+      dst[o] = v;
+    }
   }
 }
 
@@ -266,7 +272,7 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
 // routes gy to the FIRST maximum of each 2x2 window in (row, col) scan order (ATen max_pool2d backward),
 // optionally gated by x > 0 (the ReLU that produced x).
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy, bf16* __restrict__ gx, int B,
-                                    int H, int W, int cg, int relu_gate) {
+                                    int H, int W, int cg, int relu_gate, int accumulate) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -297,6 +303,16 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
     const float gv = (relu_gate && !(m > 0.f)) ? 0.f : g[j];
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? gv : 0.f;
+  }
+  if (accumulate) {
+    const size_t offs[4] = {off, off + C, off + (size_t)W * C, off + (size_t)W * C + C};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float prev[8];
+      ld8(gx + offs[k], prev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[k][j] += prev[j];
+    }
   }
   st8(gx + off, o[0]);
   st8(gx + off + C, o[1]);
@@ -392,7 +408,8 @@ __global__ void global_avgpool_lrelu_bwd_kernel(const bf16* __restrict__ x, cons
 // out = gamma * t + x   and its backward  (SelfAttention tail, models.py:274)
 // ---------------------------------------------------------------------------------------------
 __global__ void gamma_residual_fwd_kernel(const bf16* __restrict__ t, const bf16* __restrict__ x,
-                                          const float* __restrict__ gamma, bf16* __restrict__ out, long long n8) {
+                                          const float* __restrict__ gamma, bf16* __restrict__ out,
+                                          bf16* __restrict__ out_act, float slope, long long n8) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n8) return;
   const float g = __ldg(gamma);
@@ -402,6 +419,12 @@ __global__ void gamma_residual_fwd_kernel(const bf16* __restrict__ t, const bf16
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = g * a[j] + b[j];
   st8(out + idx * 8, a);
+  if (out_act != nullptr) {
+    // activate the BF16-rounded value the raw output holds
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = lrelu_f(__bfloat162float(__float2bfloat16(a[j])), slope);
+    st8(out_act + idx * 8, a);
+  }
 }
 // gt = gamma * g ; dgamma += sum(g * t)
 __global__ void gamma_residual_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ t,
@@ -514,6 +537,20 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16*
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) dst[idx] = __float2bfloat16(src[idx]);
+}
+
+__global__ void vec_epilogue_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                    const float* __restrict__ add, const float* __restrict__ gate, int mode,
+                                    float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int ld_bf16, int B, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  float v = acc[i];
+  if (bias != nullptr) v += bias[i % N];
+  if (add != nullptr) v += add[i];
+  if (mode == 1) v = fmaxf(v, 0.f);
+  if (mode == 2 && !(gate[i] > 0.f)) v = 0.f;
+  if (out_f32 != nullptr) out_f32[i] = v;
+  if (out_bf16 != nullptr) out_bf16[(size_t)(i / N) * ld_bf16 + i % N] = __float2bfloat16(v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -656,18 +693,20 @@ extern "C" int spyr_img_avgpool_pad8_bwd(const void* g8, int B, int H, int W, fl
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_nchw_to_nhwc(const float* src, const float* mask, void* dst, int B, int C, int HW, void* stream) {
+extern "C" int spyr_nchw_to_nhwc(const float* src, const float* mask, float slope, void* dst, int B, int C, int HW,
+                                 void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, (bf16*)dst, C, HW);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, slope, (bf16*)dst, C, HW);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_nhwc_to_nchw(const void* src, float* dst, int B, int C, int HW, void* stream) {
+extern "C" int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slope, float* dst, int B, int C, int HW,
+                                 void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, HW);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, gate_x, slope, dst, C, HW);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -709,11 +748,11 @@ extern "C" int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, in
   return 0;
 }
 extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B, int H, int W, int C, int relu_gate,
-                                 void* stream) {
+                                 int accumulate, void* stream) {
   SPYR_C8(C);
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gy, (bf16*)gx, B, H,
-                                                                          W, C / 8, relu_gate);
+                                                                          W, C / 8, relu_gate, accumulate);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -750,11 +789,11 @@ extern "C" int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, 
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, long long n,
-                                       void* stream) {
+extern "C" int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, void* out_act,
+                                       float slope, long long n, void* stream) {
   SPYR_REQUIRE(n % 8 == 0, "gamma_residual_fwd: n must be a multiple of 8");
-  gamma_residual_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)t, (const bf16*)x, gamma,
-                                                                                    (bf16*)out, n / 8);
+  gamma_residual_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)t, (const bf16*)x, gamma, (bf16*)out, (bf16*)out_act, slope, n / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -808,6 +847,15 @@ extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H
 }
 extern "C" int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_vec_epilogue(const float* acc, const float* bias, const float* add, const float* gate, int mode,
+                                 float* out_f32, void* out_bf16, int ld_bf16, int B, int N, void* stream) {
+  SPYR_REQUIRE(acc && (mode != 2 || gate) && (out_bf16 == nullptr || ld_bf16 >= N), "vec_epilogue: bad arguments");
+  vec_epilogue_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, bias, add, gate, mode, out_f32, (bf16*)out_bf16, ld_bf16, B, N);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

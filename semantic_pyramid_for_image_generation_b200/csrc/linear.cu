@@ -1,0 +1,225 @@
+// Small-batch ("skinny") fully connected layers in FP32 on the CUDA cores: M = batch <= 32 rows, so the work is
+// reading the weight matrix once -- HBM/L2-bound, no tensor-core tile can be filled.
+//
+// Replaces nn.Linear at models.py:28-31 (Generator.linear_layer), models.py:356,360 (LinearBlock),
+// models.py:128,132 (Discriminator head / classification) and the (B,B,128) projection of models.py:151-155.
+// Spectral normalisation is folded in: y = (x W^T) / sigma + b with sigma read from device memory.
+#include "common.cuh"
+#include "../../include/spyramid_b200.h"
+
+extern void spyr_count_launch();
+
+namespace {
+
+constexpr int LB = 8;        // batch rows per CTA
+constexpr int LROWS = 32;    // output rows per CTA (8 warps x 4)
+constexpr int LKC = 256;     // k chunk staged in shared memory
+
+__device__ __forceinline__ float in_transform(float x, const float* mask, size_t i, float slope) {
+  if (mask != nullptr) x *= mask[i];
+  return x > 0.f ? x : x * slope;  // slope == 1 -> identity
+}
+
+// y[b][o] = (sum_k f(x[b][k]) W[o][k]) * inv_sigma + bias[o]  (+ y_add[b][o]) ; optional LeakyReLU on the output
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmask, float in_slope,
+                                  const float* __restrict__ w, const float* __restrict__ sigma,
+                                  const float* __restrict__ bias, const float* __restrict__ y_add, float out_slope,
+                                  float* __restrict__ y, int B, int K, int O) {
+  __shared__ float xs[LB][LKC];
+  const int o0 = blockIdx.x * LROWS, b0 = blockIdx.y * LB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[4][LB];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int b = 0; b < LB; ++b) acc[r][b] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += LKC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < LB * LKC; i += blockDim.x) {
+      const int b = i / LKC, k = k0 + i % LKC;
+      float v = 0.f;
+      if (b0 + b < B && k < K) v = in_transform(x[(size_t)(b0 + b) * K + k], xmask, (size_t)(b0 + b) * K + k, in_slope);
+      xs[b][i % LKC] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = o0 + warp * 4 + r;
+      if (o >= O) continue;
+      const float* wp = w + (size_t)o * K + k0;
+#pragma unroll
+      for (int j = 0; j < LKC / 32; ++j) {
+        const int kk = j * 32 + lane;
+        const float wv = (k0 + kk < K) ? wp[kk] : 0.f;
+#pragma unroll
+        for (int b = 0; b < LB; ++b) acc[r][b] += wv * xs[b][kk];
+      }
+    }
+  }
+  const float inv = sigma != nullptr ? 1.f / __ldg(sigma) : 1.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = o0 + warp * 4 + r;
+#pragma unroll
+    for (int b = 0; b < LB; ++b) {
+      const float s = warp_sum(acc[r][b]);
+      if (lane == 0 && o < O && b0 + b < B) {
+        float v = s * inv + (bias != nullptr ? bias[o] : 0.f);
+        if (y_add != nullptr) v += y_add[(size_t)(b0 + b) * O + o];
+        y[(size_t)(b0 + b) * O + o] = v > 0.f ? v : v * out_slope;
+      }
+    }
+  }
+}
+
+// gx[b][k] = (sum_o gy'[b][o] W[o][k]) * inv_sigma * f'(x[b][k]),  gy' = gy * out_lrelu'(y)
+__global__ void linear_bwd_x_kernel(const float* __restrict__ gy, const float* __restrict__ y, float out_slope,
+                                    const float* __restrict__ w, const float* __restrict__ sigma,
+                                    const float* __restrict__ x, float in_slope, float* __restrict__ gx, int accumulate,
+                                    int B, int K, int O) {
+  __shared__ float gs[LB][256];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * LB;
+  float acc[LB];
+#pragma unroll
+  for (int b = 0; b < LB; ++b) acc[b] = 0.f;
+  for (int o0 = 0; o0 < O; o0 += 256) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < LB * 256; i += blockDim.x) {
+      const int b = i / 256, o = o0 + i % 256;
+      float v = 0.f;
+      if (b0 + b < B && o < O) {
+        v = gy[(size_t)(b0 + b) * O + o];
+        if (y != nullptr && !(y[(size_t)(b0 + b) * O + o] > 0.f)) v *= out_slope;
+      }
+      gs[b][i % 256] = v;
+    }
+    __syncthreads();
+    if (k < K) {
+      const int no = min(256, O - o0);
+      for (int oo = 0; oo < no; ++oo) {
+        const float wv = w[(size_t)(o0 + oo) * K + k];
+#pragma unroll
+        for (int b = 0; b < LB; ++b) acc[b] += wv * gs[b][oo];
+      }
+    }
+  }
+  if (k >= K) return;
+  const float inv = sigma != nullptr ? 1.f / __ldg(sigma) : 1.f;
+#pragma unroll
+  for (int b = 0; b < LB; ++b) {
+    if (b0 + b >= B) break;
+    float v = acc[b] * inv;
+    const size_t i = (size_t)(b0 + b) * K + k;
+    if (x != nullptr && !(x[i] > 0.f)) v *= in_slope;
+    gx[i] = accumulate ? gx[i] + v : v;
+  }
+}
+
+// gw[o][k] += sum_b gy'[b][o] f(x[b][k]);  gb[o] += sum_b gy'[b][o]      (gradient w.r.t. W / sigma)
+__global__ void linear_bwd_w_kernel(const float* __restrict__ gy, const float* __restrict__ y, float out_slope,
+                                    const float* __restrict__ x, const float* __restrict__ xmask, float in_slope,
+                                    float* __restrict__ gw, float* __restrict__ gb, int B, int K, int O) {
+  __shared__ float gs[32];
+  const int o = blockIdx.y;
+  if (threadIdx.x < 32) {
+    float v = 0.f;
+    if (threadIdx.x < B) {
+      v = gy[(size_t)threadIdx.x * O + o];
+      if (y != nullptr && !(y[(size_t)threadIdx.x * O + o] > 0.f)) v *= out_slope;
+    }
+    gs[threadIdx.x] = v;
+    const float s = warp_sum(v);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && gb != nullptr) atomicAdd(gb + o, s);
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += gs[b] * in_transform(x[(size_t)b * K + k], xmask, (size_t)b * K + k, in_slope);
+  gw[(size_t)o * K + k] += acc;
+}
+
+// out[i][j][k] = cls[j] + feat[j][k] * emb_w[idx[i]][k] / sigma          (models.py:151-155)
+__global__ void dhead_out_fwd_kernel(const float* __restrict__ cls, const float* __restrict__ feat,
+                                     const float* __restrict__ emb_w, const float* __restrict__ sigma,
+                                     const int* __restrict__ idx, float* __restrict__ out, int B, int E) {
+  const int n = B * B * E;
+  const float inv = 1.f / __ldg(sigma);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int k = t % E, j = (t / E) % B, i = t / (E * B);
+    out[t] = cls[j] + feat[(size_t)j * E + k] * emb_w[(size_t)idx[i] * E + k] * inv;
+  }
+}
+// g_cls[j] = sum_{i,k} g[i,j,k];  g_feat[j,k] = sum_i g[i,j,k] emb[i,k];  g_embw[idx[i]][k] += sum_j g[i,j,k] feat[j,k]
+__global__ void dhead_out_bwd_kernel(const float* __restrict__ g, const float* __restrict__ feat,
+                                     const float* __restrict__ emb_w, const float* __restrict__ sigma,
+                                     const int* __restrict__ idx, float* __restrict__ g_cls, float* __restrict__ g_feat,
+                                     float* __restrict__ g_embw, int B, int E) {
+  const float inv = 1.f / __ldg(sigma);
+  // one block; threads over (row, k)
+  for (int t = threadIdx.x; t < B * E; t += blockDim.x) {
+    const int r = t / E, k = t % E;
+    float gf = 0.f, ge = 0.f;
+    for (int q = 0; q < B; ++q) {
+      gf += g[((size_t)q * B + r) * E + k] * emb_w[(size_t)idx[q] * E + k] * inv;  // r plays j, q plays i
+      ge += g[((size_t)r * B + q) * E + k] * feat[(size_t)q * E + k];              // r plays i, q plays j
+    }
+    g_feat[t] = gf;
+    if (g_embw != nullptr) atomicAdd(g_embw + (size_t)idx[r] * E + k, ge);
+  }
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < B; ++i)
+      for (int k = 0; k < E; ++k) s += g[((size_t)i * B + j) * E + k];
+    g_cls[j] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" int spyr_linear_fwd(const float* x, const float* xmask, float in_slope, const float* w, const float* sigma,
+                               const float* bias, const float* y_add, float out_slope, float* y, int B, int K, int O,
+                               void* stream) {
+  SPYR_REQUIRE(x && w && y && B > 0 && K > 0 && O > 0, "linear_fwd: bad arguments");
+  dim3 grid(ceil_div(O, LROWS), ceil_div(B, LB));
+  linear_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, xmask, in_slope, w, sigma, bias, y_add, out_slope, y, B, K, O);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_linear_bwd_x(const float* gy, const float* y, float out_slope, const float* w, const float* sigma,
+                                 const float* x, float in_slope, float* gx, int accumulate, int B, int K, int O,
+                                 void* stream) {
+  SPYR_REQUIRE(gy && w && gx, "linear_bwd_x: bad arguments");
+  dim3 grid(ceil_div(K, 128), ceil_div(B, LB));
+  linear_bwd_x_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, out_slope, w, sigma, x, in_slope, gx, accumulate, B, K,
+                                                              O);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_linear_bwd_w(const float* gy, const float* y, float out_slope, const float* x, const float* xmask,
+                                 float in_slope, float* gw, float* gb, int B, int K, int O, void* stream) {
+  SPYR_REQUIRE(gy && x && gw && B <= 32, "linear_bwd_w: bad arguments (batch must be <= 32)");
+  dim3 grid(ceil_div(K, 128), O);
+  linear_bwd_w_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, out_slope, x, xmask, in_slope, gw, gb, B, K, O);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_dhead_out_fwd(const float* cls, const float* feat, const float* emb_w, const float* sigma,
+                                  const int* idx, float* out, int B, int E, void* stream) {
+  const int n = B * B * E;
+  dhead_out_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(cls, feat, emb_w, sigma, idx, out, B, E);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_dhead_out_bwd(const float* g, const float* feat, const float* emb_w, const float* sigma, const int* idx,
+                                  float* g_cls, float* g_feat, float* g_embw, int B, int E, void* stream) {
+  dhead_out_bwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(g, feat, emb_w, sigma, idx, g_cls, g_feat, g_embw, B, E);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,543 @@
+// Batch-norm / conditional batch-norm (train-mode batch statistics) fused with LeakyReLU and the
+// bilinear x2 (align_corners=True) upsampling that follows or precedes it in the generator.
+//
+// Replaces: ConditionalBatchNorm.forward (models.py:491-506), nn.BatchNorm2d(64) + nn.UpsamplingBilinear2d +
+// nn.LeakyReLU of Generator.final_block (models.py:51-54), and the CBN -> LeakyReLU -> UpsamplingBilinear2d chain
+// of GeneratorResidualBlock.main_block / residual_mapping (models.py:295-310), forward and backward.
+//
+// Affine convention shared by every entry point: scale = scale_ptr[row*row_stride + c], shift likewise,
+// row = cls[b] (class index of sample b) or 0 when cls == NULL.  CBN: scale_ptr = emb, shift_ptr = emb + C,
+// row_stride = 2C (models.py:501).  Plain BN: scale_ptr = weight, shift_ptr = bias, row_stride = 0, cls = NULL.
+#include "common.cuh"
+#include "../../include/spyramid_b200.h"
+
+extern void spyr_count_launch();
+
+namespace {
+
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// ATen upsample_bilinear2d, align_corners=True: src = dst * (in-1)/(out-1) in float
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_src(int o, int in, float scale) {
+  const float r = scale * (float)o;
+  Lerp L;
+  L.i0 = (int)r;
+  L.i1 = L.i0 + (L.i0 < in - 1 ? 1 : 0);
+  L.w1 = r - (float)L.i0;
+  L.w0 = 1.f - L.w1;
+  return L;
+}
+// hi-res positions that read low-res index j, with their weights (transpose of lerp_src)
+struct Gather {
+  int n;
+  int o[8];
+  float w[8];
+};
+__device__ __forceinline__ Gather gather_src(int j, int in, float scale) {
+  Gather G;
+  G.n = 0;
+  const int out = 2 * in;
+  int lo = (int)floorf((float)(j - 1) / scale) - 1;
+  int hi = (int)ceilf((float)(j + 1) / scale) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+  for (int o = lo; o <= hi; ++o) {
+    const Lerp L = lerp_src(o, in, scale);
+    const float w = (L.i0 == j ? L.w0 : 0.f) + (L.i1 == j ? L.w1 : 0.f);
+    if (w != 0.f && G.n < 8) {
+      G.o[G.n] = o;
+      G.w[G.n] = w;
+      ++G.n;
+    }
+  }
+  return G;
+}
+
+__device__ __forceinline__ void up2_load(const bf16* x, int b, int oh, int ow, int H, int W, int cg, int c, float sh,
+                                         float sw, float* v) {
+  const Lerp Lh = lerp_src(oh, H, sh), Lw = lerp_src(ow, W, sw);
+  float a[8], bq[8], cq[8], d[8];
+  const size_t base = (size_t)b * H * W;
+  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i0) * cg + c) * 8, a);
+  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i1) * cg + c) * 8, bq);
+  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i0) * cg + c) * 8, cq);
+  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i1) * cg + c) * 8, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = Lh.w0 * (Lw.w0 * a[j] + Lw.w1 * bq[j]) + Lh.w1 * (Lw.w0 * cq[j] + Lw.w1 * d[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W, int cg, int up2, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [prows][2][C]
+  const int C = cg * 8;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  const int OH = up2 ? 2 * H : H, OW = up2 ? 2 * W : W;
+  const float shs = up2 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float sws = up2 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const long long npix = (long long)B * OH * OW;
+  float s1[8], s2[8], v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (pr < prows)
+    for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
+      if (up2) {
+        const int ow = (int)(p % OW);
+        const int oh = (int)((p / OW) % OH);
+        const int b = (int)(p / ((long long)OW * OH));
+        up2_load(x, b, oh, ow, H, W, cg, c, shs, sws, v);
+      } else {
+        ld8(x + (p * cg + c) * 8, v);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += v[j];
+        s2[j] += v[j] * v[j];
+      }
+    }
+  if (pr < prows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sh[(pr * 2 + 0) * C + c * 8 + j] = s1[j];
+      sh[(pr * 2 + 1) * C + c * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < prows; ++r) s += (double)sh[r * 2 * C + i];
+    atomicAdd(sums + i, s);
+  }
+}
+
+// mean/rstd from the sums (train) or from the running buffers (eval); running-stat update as nn.BatchNorm2d
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float* __restrict__ mean_rstd, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    if (training) {
+      const double mean = sums[c] / count;
+      double var = sums[C + c] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_rstd[c] = (float)mean;
+      mean_rstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean != nullptr) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    } else {
+      mean_rstd[c] = running_mean[c];
+      mean_rstd[C + c] = rsqrtf(running_var[c] + eps);
+    }
+  }
+  if (training && nbt != nullptr && c == 0) *nbt += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward apply.  mode 0: a = lrelu(aff(x))            (same resolution)
+//                 mode 1: a = up2(lrelu(aff(x))), xu = up2(x)   (generator block, models.py:295-298,308)
+//                 mode 2: a = lrelu(aff(up2(x)))       (final block: upsample -> BN -> LeakyReLU, models.py:52-54)
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ mean_rstd,
+                              const float* __restrict__ scale_ptr, const float* __restrict__ shift_ptr, int row_stride,
+                              const int* __restrict__ cls, float slope, int mode, bf16* __restrict__ out_a,
+                              bf16* __restrict__ out_xu, int B, int H, int W, int cg) {
+  const int C = cg * 8;
+  const int OH = mode ? 2 * H : H, OW = mode ? 2 * W : W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int ow = (int)(t % OW);
+  t /= OW;
+  const int oh = (int)(t % OH);
+  const int b = (int)(t / OH);
+  const int row = cls != nullptr ? cls[b] : 0;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c * 8 + j;
+    const float r = mean_rstd[C + ch];
+    const float s = scale_ptr[(size_t)row * row_stride + ch] * r;
+    sc[j] = s;
+    sf[j] = shift_ptr[(size_t)row * row_stride + ch] - mean_rstd[ch] * s;
+  }
+  float v[8];
+  if (mode == 0) {
+    ld8(x + idx * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = lrelu_f(v[j] * sc[j] + sf[j], slope);
+    st8(out_a + idx * 8, v);
+    return;
+  }
+  const float shs = (float)(H - 1) / (float)(OH - 1), sws = (float)(W - 1) / (float)(OW - 1);
+  const Lerp Lh = lerp_src(oh, H, shs), Lw = lerp_src(ow, W, sws);
+  float q[4][8];
+  const size_t base = (size_t)b * H * W;
+  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i0) * cg + c) * 8, q[0]);
+  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i1) * cg + c) * 8, q[1]);
+  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i0) * cg + c) * 8, q[2]);
+  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i1) * cg + c) * 8, q[3]);
+  if (out_xu != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+    st8(out_xu + idx * 8, v);
+  }
+  if (mode == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[k][j] = lrelu_f(q[k][j] * sc[j] + sf[j], slope);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+      v[j] = lrelu_f(u * sc[j] + sf[j], slope);
+    }
+  }
+  st8(out_a + idx * 8, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, pass 1: per-(sample, channel) sums S[b][0][c] = sum_p gy, S[b][1][c] = sum_p gy * xhat.
+//   mode 0: g is already d/dy (same resolution, LeakyReLU gate applied by the conv epilogue)
+//   mode 1: g is d/da at 2H x 2W with a = up2(lrelu(y)):  gy = up2^T(g) * lrelu'(y), written to gy_out
+//   mode 2: g is d/d(pre-LeakyReLU) at 2H x 2W (gate applied upstream): gy = up2^T(g), written to gy_out
+//   mode 3: g is d/dy at 2H x 2W and the normalised tensor is up2(x) (final block): reduce at 2H x 2W
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
+                                     const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
+                                     const float* __restrict__ shift_ptr, int row_stride, const int* __restrict__ cls,
+                                     float slope, int mode, bf16* __restrict__ gy_out, float* __restrict__ S, int H, int W,
+                                     int cg) {
+  extern __shared__ float sh[];  // [prows][2][C]
+  const int C = cg * 8;
+  const int b = blockIdx.y;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  const int row = cls != nullptr ? cls[b] : 0;
+  float mu[8], rs[8], sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c * 8 + j;
+    mu[j] = mean_rstd[ch];
+    rs[j] = mean_rstd[C + ch];
+    sc[j] = scale_ptr[(size_t)row * row_stride + ch];
+    sf[j] = shift_ptr[(size_t)row * row_stride + ch];
+  }
+  const float shs = (float)(H - 1) / (float)(2 * H - 1), sws = (float)(W - 1) / (float)(2 * W - 1);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int npix = (mode == 3) ? 4 * H * W : H * W;
+  if (pr < prows)
+    for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
+      const size_t off = (((size_t)b * npix + p) * cg + c) * 8;
+      float xv[8], gy[8];
+      if (mode == 3) {
+        // statistics were taken on up2(x): reduce at the high resolution, x interpolated on the fly
+        up2_load(x, b, p / (2 * W), p % (2 * W), H, W, cg, c, shs, sws, xv);
+        ld8(g + off, gy);
+      } else if (mode == 0) {
+        ld8(x + off, xv);
+        ld8(g + off, gy);
+      } else {
+        ld8(x + off, xv);
+        const int h = p / W, w = p % W;
+        const Gather Gh = gather_src(h, H, shs), Gw = gather_src(w, W, sws);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gy[j] = 0.f;
+        for (int a = 0; a < Gh.n; ++a)
+          for (int e = 0; e < Gw.n; ++e) {
+            float gv[8];
+            ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
+            const float wt = Gh.w[a] * Gw.w[e];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gy[j] += wt * gv[j];
+          }
+        if (mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y = sc[j] * ((xv[j] - mu[j]) * rs[j]) + sf[j];
+            if (!(y > 0.f)) gy[j] *= slope;
+          }
+        }
+        // the reduction uses the BF16-rounded value that pass 2 will read back
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gy[j] = __bfloat162float(__float2bfloat16(gy[j]));
+        st8(gy_out + off, gy);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += gy[j];
+        s2[j] += gy[j] * ((xv[j] - mu[j]) * rs[j]);
+      }
+    }
+  if (pr < prows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sh[(pr * 2 + 0) * C + c * 8 + j] = s1[j];
+      sh[(pr * 2 + 1) * C + c * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < prows; ++r) s += sh[r * 2 * C + i];
+    atomicAdd(S + (size_t)b * 2 * C + i, s);
+  }
+}
+
+// pass 1b: channel means M[0][c] = (1/N) sum_b scale[b,c] S1[b,c], M[1][c] likewise with S2, and the affine
+// parameter gradients: d_scale[row(b)][c] += S2[b,c], d_shift[row(b)][c] += S1[b,c]
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C, float count,
+                                       const float* __restrict__ scale_ptr, int row_stride, const int* __restrict__ cls,
+                                       float* __restrict__ M, float* __restrict__ d_scale, float* __restrict__ d_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m1 = 0.f, m2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const int row = cls != nullptr ? cls[b] : 0;
+    const float sc = scale_ptr[(size_t)row * row_stride + c];
+    const float a1 = S[((size_t)b * 2 + 0) * C + c], a2 = S[((size_t)b * 2 + 1) * C + c];
+    m1 += sc * a1;
+    m2 += sc * a2;
+    if (d_scale != nullptr) {
+      atomicAdd(d_scale + (size_t)row * row_stride + c, a2);
+      atomicAdd(d_shift + (size_t)row * row_stride + c, a1);
+    }
+  }
+  M[c] = m1 / count;
+  M[C + c] = m2 / count;
+}
+
+// pass 2: gx = rstd * (scale * gy - M1 - xhat * M2) (+ residual).  x_up2: gy/gx live at 2H x 2W and xhat is taken
+// from up2(x) (final block, where the statistics are those of the upsampled tensor)
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ x,
+                                    const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
+                                    int row_stride, const int* __restrict__ cls, const float* __restrict__ M,
+                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int B, int H, int W, int cg,
+                                    int x_up2) {
+  const int C = cg * 8;
+  const int OH = x_up2 ? 2 * H : H, OW = x_up2 ? 2 * W : W;
+  const long long HW = (long long)OH * OW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW * cg) return;
+  const int c = (int)(idx % cg);
+  const int b = (int)(idx / (HW * cg));
+  const int row = cls != nullptr ? cls[b] : 0;
+  float g[8], xv[8], o[8];
+  ld8(gy + idx * 8, g);
+  if (x_up2) {
+    const long long p = (idx / cg) % HW;
+    up2_load(x, b, (int)(p / OW), (int)(p % OW), H, W, cg, c, (float)(H - 1) / (float)(OH - 1),
+             (float)(W - 1) / (float)(OW - 1), xv);
+  } else {
+    ld8(x + idx * 8, xv);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c * 8 + j;
+    const float r = mean_rstd[C + ch];
+    const float xh = (xv[j] - mean_rstd[ch]) * r;
+    o[j] = r * (scale_ptr[(size_t)row * row_stride + ch] * g[j] - M[ch] - xh * M[C + ch]);
+  }
+  if (residual != nullptr) {
+    float rv[8];
+    ld8(residual + idx * 8, rv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += rv[j];
+  }
+  st8(gx + idx * 8, o);
+}
+
+// plain transposed bilinear x2 (align_corners=True): g_lo = up2^T(g_hi)  (skip path of the generator block)
+__global__ void up2_bwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ out, int B, int H, int W, int cg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * cg) return;
+  const int c = (int)(idx % cg);
+  long long t = idx / cg;
+  const int w = (int)(t % W);
+  t /= W;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  const float shs = (float)(H - 1) / (float)(2 * H - 1), sws = (float)(W - 1) / (float)(2 * W - 1);
+  const Gather Gh = gather_src(h, H, shs), Gw = gather_src(w, W, sws);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int a = 0; a < Gh.n; ++a)
+    for (int e = 0; e < Gw.n; ++e) {
+      float gv[8];
+      ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
+      const float wt = Gh.w[a] * Gw.w[e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wt * gv[j];
+    }
+  st8(out + idx * 8, acc);
+}
+
+// class index of each one-hot row (class_id.argmax(dim=-1), models.py:151,501); first maximum wins like torch
+template <typename T>
+__global__ void argmax_rows_kernel(const T* __restrict__ onehot, int n, int* __restrict__ out) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int best = 0;
+    T m = onehot[(size_t)b * n];
+    for (int i = 1; i < n; ++i) {
+      const T v = onehot[(size_t)b * n + i];
+      if (v > m) {
+        m = v;
+        best = i;
+      }
+    }
+    out[b] = best;
+  }
+}
+
+struct Threads {
+  int prows, threads;
+};
+inline Threads pick_threads(int cg, int max_threads) {
+  Threads t;
+  t.prows = max_threads / cg;
+  if (t.prows < 1) t.prows = 1;
+  t.threads = t.prows * cg;
+  return t;
+}
+
+}  // namespace
+
+#define SPYR_C8(C) SPYR_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channel count %d must be a multiple of 8", __func__, (int)(C))
+
+extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPYR_C8(C);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 256, "bn_stats: C=%d too large", C);
+  SPYR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  const Threads t = pick_threads(cg, 256);
+  const long long npix = (long long)B * H * W * (up2 ? 4 : 1);
+  long long want = (npix + t.prows * 16 - 1) / (t.prows * 16);
+  const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  bn_stats_kernel<<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, up2, sums);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                                float* running_var, long long* num_batches_tracked, float* mean_rstd, int training,
+                                void* stream) {
+  SPYR_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, C, eps, momentum, running_mean,
+                                                                         running_var, num_batches_tracked, mean_rstd,
+                                                                         training);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr,
+                           int row_stride, const int* cls, float slope, int mode, void* out_a, void* out_xu, int B, int H,
+                           int W, int C, void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(mode >= 0 && mode <= 2, "bn_act: bad mode %d", mode);
+  SPYR_REQUIRE(mode == 0 || (H > 1 && W > 1), "bn_act: upsampling needs H,W > 1");
+  const long long n = (long long)B * H * W * (mode ? 4 : 1) * (C / 8);
+  bn_act_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr,
+                                                                          row_stride, cls, slope, mode, (bf16*)out_a,
+                                                                          (bf16*)out_xu, B, H, W, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr,
+                                  const float* shift_ptr, int row_stride, const int* cls, float slope, int mode,
+                                  void* gy_out, float* S, int B, int H, int W, int C, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPYR_C8(C);
+  SPYR_REQUIRE(mode == 0 || mode == 3 || gy_out != nullptr, "bn_bwd_reduce: modes 1/2 need gy_out");
+  SPYR_REQUIRE(mode >= 0 && mode <= 3, "bn_bwd_reduce: bad mode %d", mode);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 256, "bn_bwd_reduce: C=%d too large", C);
+  SPYR_CHECK_CUDA(cudaMemsetAsync(S, 0, sizeof(float) * 2 * C * B, stream));
+  const Threads t = pick_threads(cg, 256);
+  const int npix = H * W * (mode == 3 ? 4 : 1);
+  int gx = (npix + t.prows * 8 - 1) / (t.prows * 8);
+  const int cap = (1184 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  bn_bwd_reduce_kernel<<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(
+      (const bf16*)g, (const bf16*)x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, mode, (bf16*)gy_out, S, H, W,
+      cg);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_bn_bwd_finalize(const float* S, int B, int C, float count, const float* scale_ptr, int row_stride,
+                                    const int* cls, float* M, float* d_scale, float* d_shift, void* stream) {
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(S, B, C, count, scale_ptr, row_stride, cls, M,
+                                                                             d_scale, d_shift);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mean_rstd, const float* scale_ptr,
+                                 int row_stride, const int* cls, const float* M, const void* residual, void* gx, int B,
+                                 int H, int W, int C, int x_up2, void* stream) {
+  SPYR_C8(C);
+  const long long n = (long long)B * H * W * (C / 8) * (x_up2 ? 4 : 1);
+  bn_bwd_apply_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, B, H, W,
+      C / 8, x_up2);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_up2_bwd(const void* g_hi, void* g_lo, int B, int H, int W, int C, void* stream) {
+  SPYR_C8(C);
+  SPYR_REQUIRE(H > 1 && W > 1, "up2_bwd: H,W must be > 1");
+  const long long n = (long long)B * H * W * (C / 8);
+  up2_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g_hi, (bf16*)g_lo, B, H, W, C / 8);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_argmax_rows(const void* onehot, int is_int64, int B, int n, int* out, void* stream) {
+  if (is_int64)
+    argmax_rows_kernel<long long><<<B, 32, 0, (cudaStream_t)stream>>>((const long long*)onehot, n, out);
+  else
+    argmax_rows_kernel<float><<<B, 32, 0, (cudaStream_t)stream>>>((const float*)onehot, n, out);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}

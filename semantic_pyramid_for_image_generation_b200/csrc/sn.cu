@@ -1,0 +1,299 @@
+// Spectral normalisation for ALL layers of a model in three launches per forward (plus two per backward).
+//
+// Replaces torch.nn.utils.spectral_norm (torch/nn/utils/spectral_norm.py:92-114) at every call site in the
+// reference (models.py:28,34,55,58,128,132,135,232-243,299-313,356-360,393-403,438-448):
+//   train : v <- normalize(W^T u), u <- normalize(W v)   (one power iteration, in place, eps 1e-12)
+//           sigma = u . (W v);  the layer then uses W / sigma
+//   eval  : sigma from the stored u, v (no iteration)
+// and emits, in the same pass, the BF16 operand the tensor-core convolutions consume:
+//   packed[tap][cout][cin] = bf16(W[cout][cin][tap] / sigma)      (see spyr_conv_src.w)
+// plus, for the `cat(feature*mask, mask)` convolutions (models.py:94,312-315), the FP32 taps of the extra mask
+// channel as stencil[10][cout] (9 taps + their sum).
+// Backward: dL/dW = (G - <G, W/sigma> u v^T) / sigma with u, v treated as constants (they are detached clones in
+// torch), G given either in W's own layout or in the wgrad kernel's [tap][cin][cout] layout.
+#include "common.cuh"
+#include "../../include/spyramid_b200.h"
+
+extern void spyr_count_launch();
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ int find_layer(const spyr_sn_layer* tab, int n, int tile, int which, int* sh_idx) {
+  if (threadIdx.x == 0) {
+    int l = 0;
+    for (int i = 0; i < n; ++i) {
+      const int t0 = which == 0 ? tab[i].tile0_wtu : (which == 1 ? tab[i].tile0_wv : (which == 2 ? tab[i].tile0_pack : tab[i].tile0_bwd));
+      if (t0 <= tile) l = i;
+    }
+    *sh_idx = l;
+  }
+  __syncthreads();
+  return *sh_idx;
+}
+
+constexpr int WTU_ROWS = 64, WTU_COLS = 256;
+
+// t[j] += sum_{i in tile rows} W[i][j] u[i]
+__global__ void sn_wtu_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch) {
+  __shared__ int sh_idx;
+  __shared__ float su[WTU_ROWS];
+  const int l = find_layer(tab, n, blockIdx.x, 0, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  const int tile = blockIdx.x - L.tile0_wtu;
+  const int ctiles = (L.cols + WTU_COLS - 1) / WTU_COLS;
+  const int r0 = (tile / ctiles) * WTU_ROWS, c0 = (tile % ctiles) * WTU_COLS;
+  const int nr = min(WTU_ROWS, L.rows - r0);
+  if (threadIdx.x < nr) su[threadIdx.x] = L.u[r0 + threadIdx.x];
+  __syncthreads();
+  const int j = c0 + threadIdx.x;
+  if (j >= L.cols) return;
+  const float* wp = L.w + (size_t)r0 * L.cols + j;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < nr; ++i) acc += wp[(size_t)i * L.cols] * su[i];
+  atomicAdd(scratch + L.scratch_off + j, acc);
+}
+
+constexpr int WV_ROWS = 32;
+
+// s[i] = sum_j W[i][j] v[j], v = t / max(|t|, eps) (train) or the stored v (eval); one CTA also stores v
+__global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch, int training,
+                             float eps) {
+  __shared__ int sh_idx;
+  __shared__ float red[32];
+  const int l = find_layer(tab, n, blockIdx.x, 1, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  const int tile = blockIdx.x - L.tile0_wv;
+  const int r0 = tile * WV_ROWS;
+  const float* vec;
+  float vscale = 1.f;
+  if (training) {
+    const float* t = scratch + L.scratch_off;
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < L.cols; j += blockDim.x) ss += t[j] * t[j];
+    ss = block_sum(ss, red);
+    vscale = 1.f / fmaxf(sqrtf(ss), eps);
+    vec = t;
+    if (tile == 0)
+      for (int j = threadIdx.x; j < L.cols; j += blockDim.x) L.v[j] = t[j] * vscale;
+  } else {
+    vec = L.v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_warp = WV_ROWS / (blockDim.x >> 5);
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int i = r0 + warp * rows_per_warp + rr;
+    if (i >= L.rows) break;
+    const float* wp = L.w + (size_t)i * L.cols;
+    float acc = 0.f;
+    for (int j = lane; j < L.cols; j += 32) acc += wp[j] * vec[j];
+    acc = warp_sum(acc) * vscale;
+    if (lane == 0) scratch[L.scratch_off + L.cols + i] = acc;
+  }
+}
+
+// sigma, u update, saved copies, BF16 pack.  One CTA per weight row (pack layers) or one CTA per layer.
+__global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, const float* __restrict__ scratch,
+                               int training, float eps, bf16* __restrict__ packed, float* __restrict__ stencil,
+                               float* __restrict__ saved) {
+  __shared__ int sh_idx;
+  __shared__ float red[32];
+  const int l = find_layer(tab, n, blockIdx.x, 2, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  const int tile = blockIdx.x - L.tile0_pack;
+  const float* s = scratch + L.scratch_off + L.cols;
+  float sigma, uscale = 1.f;
+  if (training) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < L.rows; i += blockDim.x) ss += s[i] * s[i];
+    ss = block_sum(ss, red);
+    uscale = 1.f / fmaxf(sqrtf(ss), eps);
+    sigma = ss * uscale;  // u . s with u = s * uscale
+  } else {
+    float d = 0.f;
+    for (int i = threadIdx.x; i < L.rows; i += blockDim.x) d += L.u[i] * s[i];
+    sigma = block_sum(d, red);
+  }
+  float* sv = saved + L.saved_off;
+  if (tile == 0) {
+    // after the block_sum barrier every thread of this CTA has finished reading L.u
+    for (int i = threadIdx.x; i < L.rows; i += blockDim.x) {
+      const float un = training ? s[i] * uscale : L.u[i];
+      if (training) L.u[i] = un;
+      sv[1 + i] = un;
+    }
+    for (int j = threadIdx.x; j < L.cols; j += blockDim.x) sv[1 + L.rows + j] = L.v[j];
+    if (threadIdx.x == 0) sv[0] = sigma;
+  }
+  if (L.pack_cin <= 0) return;
+  const float inv = 1.f / sigma;
+  const int co = tile;
+  const float* wrow = L.w + (size_t)co * L.cols;
+  bf16* dst = packed + L.pack_off;
+  const int taps = L.taps, pc = L.pack_cin;
+  if (L.pack_mode == 1) {
+    // im2col rows: packed[co][k], k = t*cin + ci, zero padded to pack_cin columns
+    for (int k = threadIdx.x; k < pc; k += blockDim.x) {
+      float v = 0.f;
+      if (k < L.cols) v = wrow[(k % L.cin) * taps + k / L.cin] * inv;
+      dst[(size_t)co * pc + k] = __float2bfloat16(v);
+    }
+    return;
+  }
+  // packed[t][co][ci], ci < pack_cin
+  for (int i = threadIdx.x; i < taps * pc; i += blockDim.x) {
+    const int t = i / pc, ci = i % pc;
+    dst[((size_t)t * L.rows + co) * pc + ci] = __float2bfloat16(wrow[ci * taps + t] * inv);
+  }
+  if (L.stencil_off >= 0 && threadIdx.x < 32) {
+    // extra (mask) input channel pack_cin: FP32 taps + their sum
+    float* st = stencil + L.stencil_off;
+    float v = 0.f;
+    if (threadIdx.x < taps) {
+      v = wrow[pc * taps + threadIdx.x] * inv;
+      st[(size_t)threadIdx.x * L.rows + co] = v;
+    }
+    v = warp_sum(v);
+    if (threadIdx.x == 0) st[(size_t)9 * L.rows + co] = v;
+  }
+}
+
+constexpr int BT = 32;  // backward tile: 32 rows (cout) x 32 input channels x taps
+
+// pass 1: dots[l] += sum G * W      pass 2: out = (G - dots/sigma * u v^T) / sigma
+template <int PASS>
+__global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, const float* __restrict__ gw_arena,
+                              const float* __restrict__ saved, float* __restrict__ dots, float* __restrict__ grad_arena) {
+  extern __shared__ float gsh[];  // [taps][BT ci][BT+1 co]
+  __shared__ int sh_idx;
+  __shared__ float red[32];
+  const int l = find_layer(tab, n, blockIdx.x, 3, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  if (L.gw_off < 0) return;
+  const int tile = blockIdx.x - L.tile0_bwd;
+  const int ctiles = (L.cin + BT - 1) / BT;
+  const int co0 = (tile / ctiles) * BT, ci0 = (tile % ctiles) * BT;
+  const int nco = min(BT, L.rows - co0), nci = min(BT, L.cin - ci0);
+  const float* gw = gw_arena + L.gw_off;
+  const int taps = L.taps;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (L.gw_layout == 1) {
+    // coalesced along cout
+    for (int r = wid; r < taps * nci; r += nw) {
+      const int t = r / nci, ci = r % nci;
+      if (lane < nco) gsh[(t * BT + ci) * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
+    }
+  } else {
+    for (int r = wid; r < nco; r += nw)
+      for (int e = lane; e < nci * taps; e += 32) {
+        const int ci = e / taps, t = e % taps;
+        gsh[(t * BT + ci) * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
+      }
+  }
+  __syncthreads();
+  const float* sv = saved + L.saved_off;
+  const float sigma = sv[0];
+  if (PASS == 1) {
+    float acc = 0.f;
+    for (int r = wid; r < nco; r += nw) {
+      const float* wrow = L.w + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
+      for (int e = lane; e < nci * taps; e += 32) {
+        const int ci = e / taps, t = e % taps;
+        acc += gsh[(t * BT + ci) * (BT + 1) + r] * wrow[e];
+      }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(dots + L.index, acc);
+  } else {
+    const float inv = 1.f / sigma;
+    const float coef = dots[L.index] * inv;  // <G, W/sigma>
+    float* out = grad_arena + L.grad_off;
+    for (int r = wid; r < nco; r += nw) {
+      const float ur = sv[1 + co0 + r] * coef;
+      float* orow = out + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
+      const float* vv = sv + 1 + L.rows + (size_t)ci0 * taps;
+      for (int e = lane; e < nci * taps; e += 32) {
+        const int ci = e / taps, t = e % taps;
+        orow[e] = (gsh[(t * BT + ci) * (BT + 1) + r] - ur * vv[e]) * inv;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
+  SPYR_REQUIRE(tab != nullptr && out != nullptr && n > 0, "sn_plan: bad arguments");
+  int t_wtu = 0, t_wv = 0, t_pack = 0, t_bwd = 0;
+  long long scratch = 0, saved = 0;
+  for (int i = 0; i < n; ++i) {
+    spyr_sn_layer& L = tab[i];
+    SPYR_REQUIRE(L.rows > 0 && L.cols > 0 && L.taps > 0 && L.cin * L.taps == L.cols, "sn_plan: layer %d has bad shape", i);
+    SPYR_REQUIRE(L.taps <= 9, "sn_plan: layer %d has %d taps", i, L.taps);
+    L.index = i;
+    L.tile0_wtu = t_wtu;
+    t_wtu += ceil_div(L.rows, WTU_ROWS) * ceil_div(L.cols, WTU_COLS);
+    L.tile0_wv = t_wv;
+    t_wv += ceil_div(L.rows, WV_ROWS);
+    L.tile0_pack = t_pack;
+    t_pack += L.pack_cin > 0 ? L.rows : 1;
+    L.tile0_bwd = t_bwd;
+    t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, BT);
+    L.scratch_off = scratch;
+    scratch += L.cols + L.rows;
+    L.saved_off = saved;
+    saved += 1 + L.rows + L.cols;
+  }
+  out->tiles_wtu = t_wtu;
+  out->tiles_wv = t_wv;
+  out->tiles_pack = t_pack;
+  out->tiles_bwd = t_bwd;
+  out->scratch_floats = scratch;
+  out->saved_floats = saved;
+  return 0;
+}
+
+extern "C" int spyr_sn_forward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, int training, float eps,
+                               float* scratch, void* packed, float* stencil, float* saved, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPYR_REQUIRE(dev_tab && plan && scratch && saved && n > 0, "sn_forward: bad arguments");
+  if (training) {
+    SPYR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * plan->scratch_floats, stream));
+    sn_wtu_kernel<<<plan->tiles_wtu, WTU_COLS, 0, stream>>>(dev_tab, n, scratch);
+    spyr_count_launch();
+    SPYR_LAUNCH_CHECK();
+  }
+  sn_wv_kernel<<<plan->tiles_wv, 256, 0, stream>>>(dev_tab, n, scratch, training, eps);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  sn_pack_kernel<<<plan->tiles_pack, 128, 0, stream>>>(dev_tab, n, scratch, training, eps, (bf16*)packed, stencil, saved);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int spyr_sn_backward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, const float* gw_arena,
+                                const float* saved, float* dots, float* grad_arena, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPYR_REQUIRE(dev_tab && plan && gw_arena && saved && dots && grad_arena, "sn_backward: bad arguments");
+  SPYR_CHECK_CUDA(cudaMemsetAsync(dots, 0, sizeof(float) * n, stream));
+  const size_t smem = (size_t)9 * BT * (BT + 1) * sizeof(float);
+  sn_bwd_kernel<1><<<plan->tiles_bwd, 256, smem, stream>>>(dev_tab, n, gw_arena, saved, dots, grad_arena);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  sn_bwd_kernel<2><<<plan->tiles_bwd, 256, smem, stream>>>(dev_tab, n, gw_arena, saved, dots, grad_arena);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,210 @@
+"""Thin tensor-level wrappers over the C-ABI kernels (allocation + argument marshalling only).
+
+Feature maps are torch tensors of shape (B, H, W, C), dtype bfloat16, contiguous (NHWC).  Vectors, statistics,
+losses and master weights are float32.  Nothing here computes on the host or through torch kernels.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+from ._native import call, ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+LRELU = 0.2
+
+
+def empty_bf16(*shape, device=None):
+    return torch.empty(shape, dtype=BF16, device=device or "cuda")
+
+
+def empty_f32(*shape, device=None):
+    return torch.empty(shape, dtype=F32, device=device or "cuda")
+
+
+def zeros_f32(*shape, device=None):
+    return torch.zeros(shape, dtype=F32, device=device or "cuda")
+
+
+class Src(object):
+    """One accumulation source of a tensor-core convolution (see spyr_conv_src)."""
+    __slots__ = ("x", "w", "cin", "ksize", "mn", "per_image")
+
+    def __init__(self, x, w, cin, ksize, mn=False, per_image=False):
+        self.x, self.w, self.cin, self.ksize, self.mn, self.per_image = x, w, cin, ksize, mn, per_image
+
+
+def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=None, stencil_w=None, dmask=None, dmask_slope=1.0, residual=None,
+         want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None):
+    """out = sum_src conv(src) (+bias, mask stencil, gate, residual).  Returns (y_raw, y_act) (None when not asked).
+
+    `w` of a source may be a tensor or an int device address (a slice of a packed-weight arena)."""
+    d = N.ConvDesc()
+    d.B, d.H, d.W, d.Cout, d.nsrc = B, H, W, Cout, len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i].x = s.x.data_ptr()
+        d.src[i].w = s.w if isinstance(s.w, int) else s.w.data_ptr()
+        d.src[i].cin, d.src[i].ksize = s.cin, s.ksize
+        d.src[i].w_mn_major, d.src[i].w_per_image = int(s.mn), int(s.per_image)
+    dev = device or srcs[0].x.device
+    d.bias = bias if isinstance(bias, int) else ptr(bias)
+    d.bias2, d.bias3 = ptr(bias2), ptr(bias3)
+    d.stencil_mask = ptr(stencil_mask)
+    d.stencil_w = stencil_w if isinstance(stencil_w, int) else ptr(stencil_w)
+    d.dmask, d.dmask_slope = ptr(dmask), dmask_slope
+    d.residual = ptr(residual)
+    y_raw = y_act = None
+    if f32_out is not None:
+        d.y_f32, d.f32_store, d.splits = f32_out.data_ptr(), int(f32_store), splits
+    else:
+        if want_raw:
+            y_raw = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+            d.y_raw = y_raw.data_ptr()
+        if want_act:
+            y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+            d.y_act = y_act.data_ptr()
+        d.act, d.act_slope = act, act_slope
+    call("spyr_conv2d_fprop", C.byref(d))
+    return y_raw, y_act
+
+
+def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=False):
+    """dw[tap][ci][co] += sum_pixels x[p+tap][ci] * dy[p][co]  (FP32 accumulate into a zero-filled arena slice)."""
+    d = N.WgradDesc()
+    d.B, d.H, d.W, d.Cin, d.Cout, d.ksize = B, H, W, Cin, Cout, ksize
+    d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw_ptr
+    d.cin_stride, d.per_image = cin_stride, int(per_image)
+    call("spyr_conv2d_wgrad", C.byref(d))
+
+
+def colsum(g, C_, out0, out1=None, out2=None):
+    rows = g.numel() // C_
+    call("spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2)
+
+
+def maskgate(f, mask):
+    out = torch.empty_like(f)
+    call("spyr_maskgate", f.data_ptr(), mask.data_ptr(), out.data_ptr(), f.numel() // f.shape[-1], f.shape[-1])
+    return out
+
+
+def nchw_to_nhwc(src, mask=None, slope=1.0):
+    B, Cc, H, W = src.shape
+    out = torch.empty((B, H, W, Cc), dtype=BF16, device=src.device)
+    call("spyr_nchw_to_nhwc", src.data_ptr(), ptr(mask), slope, out.data_ptr(), B, Cc, H * W)
+    return out
+
+
+def nhwc_to_nchw(src, gate_x=None, slope=1.0):
+    B, H, W, Cc = src.shape
+    out = torch.empty((B, Cc, H, W), dtype=F32, device=src.device)
+    call("spyr_nhwc_to_nchw", src.data_ptr(), ptr(gate_x), slope, out.data_ptr(), B, Cc, H * W)
+    return out
+
+
+def as_nhwc_bf16(t, mask=None):
+    """Accepts an NCHW-shaped tensor: a permuted view of NHWC BF16 storage is used in place, anything else is
+    converted (FP32 NCHW -> BF16 NHWC).  The optional (B,1,H,W) mask gates the feature (models.py:94)."""
+    if t.dtype == BF16 and t.dim() == 4:
+        v = t.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return maskgate(v, mask) if mask is not None else v
+    if t.dtype != F32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return nchw_to_nhwc(t, mask)
+
+
+def avgpool2(x, residual=None, want_raw=True, want_act=False, slope=LRELU):
+    B, H, W, Cc = x.shape
+    y_raw = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device) if want_raw else None
+    y_act = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device) if want_act else None
+    call("spyr_avgpool2_fwd", x.data_ptr(), ptr(residual), ptr(y_raw), ptr(y_act), slope, B, H, W, Cc)
+    return y_raw, y_act
+
+
+def avgpool2_bwd(g_lo):
+    B, h, w, Cc = g_lo.shape
+    g_hi = torch.empty((B, 2 * h, 2 * w, Cc), dtype=BF16, device=g_lo.device)
+    call("spyr_avgpool2_bwd", g_lo.data_ptr(), g_hi.data_ptr(), B, 2 * h, 2 * w, Cc)
+    return g_hi
+
+
+def maxpool2(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    call("spyr_maxpool2_fwd", x.data_ptr(), y.data_ptr(), B, H, W, Cc)
+    return y
+
+
+def maxpool2_bwd(x, gy, relu_gate, out=None):
+    B, H, W, Cc = x.shape
+    acc = out is not None
+    gx = out if acc else torch.empty_like(x)
+    call("spyr_maxpool2_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), B, H, W, Cc, int(relu_gate), int(acc))
+    return gx
+
+
+def bn_stats(x, up2=False):
+    B, H, W, Cc = x.shape
+    sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
+    call("spyr_bn_stats", x.data_ptr(), B, H, W, Cc, int(up2), sums.data_ptr())
+    return sums
+
+
+def bn_finalize(sums, count, Cc, eps, momentum, running_mean, running_var, nbt, training):
+    mean_rstd = torch.empty(2 * Cc, dtype=F32, device=running_mean.device if running_mean is not None else sums.device)
+    call("spyr_bn_finalize", ptr(sums), float(count), Cc, eps, momentum, ptr(running_mean), ptr(running_var), ptr(nbt),
+         mean_rstd.data_ptr(), int(training))
+    return mean_rstd
+
+
+def bn_act(x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, mode, want_xu=False, slope=LRELU):
+    B, H, W, Cc = x.shape
+    f = 2 if mode else 1
+    a = torch.empty((B, H * f, W * f, Cc), dtype=BF16, device=x.device)
+    xu = torch.empty((B, H * f, W * f, Cc), dtype=BF16, device=x.device) if want_xu else None
+    call("spyr_bn_act", x.data_ptr(), mean_rstd.data_ptr(), scale_ptr, shift_ptr, row_stride, ptr(cls), slope, mode,
+         a.data_ptr(), ptr(xu), B, H, W, Cc)
+    return a, xu
+
+
+def linear_fwd(x, w, sigma_ptr, bias, xmask=None, in_slope=1.0, y_add=None, out_slope=1.0):
+    B, K = x.shape
+    O = w.shape[0]
+    y = torch.empty((B, O), dtype=F32, device=x.device)
+    call("spyr_linear_fwd", x.data_ptr(), ptr(xmask), in_slope, w.data_ptr(), sigma_ptr, ptr(bias), ptr(y_add), out_slope,
+         y.data_ptr(), B, K, O)
+    return y
+
+
+def linear_bwd_x(gy, w, sigma_ptr, y=None, out_slope=1.0, x=None, in_slope=1.0, out=None):
+    B, O = gy.shape
+    K = w.shape[1]
+    acc = out is not None
+    gx = out if acc else torch.empty((B, K), dtype=F32, device=gy.device)
+    call("spyr_linear_bwd_x", gy.data_ptr(), ptr(y), out_slope, w.data_ptr(), sigma_ptr, ptr(x), in_slope, gx.data_ptr(),
+         int(acc), B, K, O)
+    return gx
+
+
+def linear_bwd_w(gy, x, gw_ptr, gb_ptr, y=None, out_slope=1.0, xmask=None, in_slope=1.0):
+    B, O = gy.shape
+    K = x.shape[1]
+    call("spyr_linear_bwd_w", gy.data_ptr(), ptr(y), out_slope, x.data_ptr(), ptr(xmask), in_slope, gw_ptr, gb_ptr, B, K, O)
+
+
+def argmax_rows(onehot):
+    B, n = onehot.shape
+    if onehot.dtype not in (F32, torch.int64):
+        onehot = onehot.float()
+    onehot = onehot.contiguous()
+    out = torch.empty(B, dtype=torch.int32, device=onehot.device)
+    call("spyr_argmax_rows", onehot.data_ptr(), int(onehot.dtype == torch.int64), B, n, out.data_ptr())
+    return out
+
+
+def cast_bf16(src):
+    out = torch.empty(src.shape, dtype=BF16, device=src.device)
+    call("spyr_cast_f32_bf16", src.data_ptr(), out.data_ptr(), src.numel())
+    return out

@@ -1,0 +1,162 @@
+"""VGG-16 feature-pyramid encoder (frozen weights) on the tensor-core conv kernels.
+
+Mirrors VGG16.forward (reference models.py:183-216): ImageNet normalisation of the [-1,1] image as is
+(SURVEY Q8), 13 conv3x3+ReLU, a tap after each of the five max-pools, adaptive 7x7 average pool, fc6 / fc7 / fc8
+with taps at classifier index 3 (which the following in-place ReLU turns into ReLU(fc7)) and 6.
+Weights are frozen (model_wrapper.py:67-68), so they are packed to BF16 once; only input gradients are computed.
+"""
+import torch
+
+from . import ops
+from ._native import call
+from .ops import Src
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28)
+POOL_AFTER = (1, 3, 6, 9, 12)  # positions in CONV_IDX followed by MaxPool2d(2)
+
+
+class VGGPack(object):
+    """BF16 operands of the frozen network (built once per weight version)."""
+
+    def __init__(self, vgg16):
+        dev = vgg16.features[0].weight.device
+        self.w, self.b, self.ch = [], [], []
+        for j, idx in enumerate(CONV_IDX):
+            conv = vgg16.features[idx]
+            w = conv.weight.detach().float()
+            cout, cin = w.shape[0], w.shape[1]
+            if j == 0:
+                # im2col operand [cout][32]: k = tap*3 + c
+                pk = torch.zeros(cout, 32, dtype=F32, device=dev)
+                pk[:, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
+            else:
+                pk = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+            self.w.append(pk.to(BF16).contiguous())
+            self.b.append(conv.bias.detach().float().contiguous())
+            self.ch.append((cin, cout))
+        fc6, fc7, fc8 = vgg16.classifier[0], vgg16.classifier[3], vgg16.classifier[6]
+        c5 = self.ch[-1][1]
+        w6 = fc6.weight.detach().float()
+        # torch flattens (C,7,7); the NHWC pipeline flattens (7,7,C)
+        w6 = w6.view(w6.shape[0], c5, 7, 7).permute(0, 2, 3, 1).reshape(w6.shape[0], -1)
+        n8 = fc8.weight.shape[0]
+        self.n8, self.n8_pad = n8, (n8 + 7) // 8 * 8
+        w8 = torch.zeros(self.n8_pad, fc8.weight.shape[1], dtype=F32, device=dev)
+        w8[:n8] = fc8.weight.detach().float()
+        self.fc_w = [w6.to(BF16).contiguous(), fc7.weight.detach().to(BF16).contiguous(), w8.to(BF16).contiguous()]
+        self.fc_b = [m.bias.detach().float().contiguous() for m in (fc6, fc7, fc8)]
+        self.mean = torch.tensor([0.485, 0.456, 0.406], dtype=F32, device=dev)
+        self.invstd = 1.0 / torch.tensor([0.229, 0.224, 0.225], dtype=F32, device=dev)
+
+
+def _splits(ktotal, ntiles, mtiles=1):
+    s = max(1, 148 // max(1, ntiles * mtiles))
+    return min(s, ktotal)
+
+
+def _fc_forward(x_bf16, w, bias, B, K, O, relu, dev, want_bf16=True):
+    acc = torch.zeros((B, O), dtype=F32, device=dev)
+    ops.conv(B, 1, 1, O, [Src(x_bf16, w, K, 1)], f32_out=acc, splits=_splits(K // 64, (O + 255) // 256))
+    y = torch.empty((B, O), dtype=F32, device=dev)
+    yb = torch.empty((B, O), dtype=BF16, device=dev) if want_bf16 else None
+    call("spyr_vec_epilogue", acc.data_ptr(), bias.data_ptr(), None, None, 1 if relu else 0, y.data_ptr(),
+         yb.data_ptr() if want_bf16 else None, O, B, O)
+    return y, yb
+
+
+def vgg_forward(pk, img, save):
+    """img: (B,3,H,W) FP32 NCHW.  Returns ([p1..p5] NHWC BF16, fc7 post-ReLU (B,4096) FP32, logits (B,365) FP32), ctx."""
+    B, Ci, H, W = img.shape
+    dev = img.device
+    col = torch.empty((B, H, W, 32), dtype=BF16, device=dev)
+    call("spyr_im2col3x3", img.data_ptr(), B, H, W, pk.mean.data_ptr(), pk.invstd.data_ptr(), col.data_ptr())
+    acts, pools = [], []
+    h, w = H, W
+    x = col
+    for j, (cin, cout) in enumerate(pk.ch):
+        src = Src(x, pk.w[j], 32, 1) if j == 0 else Src(x, pk.w[j], cin, 3)
+        _, x = ops.conv(B, h, w, cout, [src], bias=pk.b[j], want_raw=False, want_act=True, act=1)
+        acts.append(x)
+        if j in POOL_AFTER:
+            x = ops.maxpool2(x)
+            pools.append(x)
+            h, w = h // 2, w // 2
+    c5 = pk.ch[-1][1]
+    pooled = torch.empty((B, 7, 7, c5), dtype=BF16, device=dev)
+    call("spyr_adaptive_avgpool_fwd", x.data_ptr(), pooled.data_ptr(), B, h, w, 7, 7, c5)
+    K6 = 49 * c5
+    y6, y6b = _fc_forward(pooled, pk.fc_w[0], pk.fc_b[0], B, K6, pk.fc_w[0].shape[0], True, dev)
+    y7, y7b = _fc_forward(y6b, pk.fc_w[1], pk.fc_b[1], B, pk.fc_w[1].shape[1], pk.fc_w[1].shape[0], True, dev)
+    y8, _ = _fc_forward(y7b, pk.fc_w[2], pk.fc_b[2], B, pk.fc_w[2].shape[1], pk.n8, False, dev, want_bf16=False)
+    ctx = (col, acts, pools, y6, y7, (B, H, W)) if save else None
+    return pools, y7, y8, ctx
+
+
+def _fc_dgrad(g_bf16, w, B, K, O, dev):
+    """g (B,1,1,K) @ W[K][O] -> FP32 (B,O) via the MN-major view of the forward pack."""
+    acc = torch.zeros((B, O), dtype=F32, device=dev)
+    ops.conv(B, 1, 1, O, [Src(g_bf16, w, K, 1, mn=True)], f32_out=acc, splits=_splits(K // 64, (O + 255) // 256))
+    return acc
+
+
+def vgg_backward(pk, ctx, g_pools, g7, g8):
+    """d/dimage (NCHW FP32) from the gradients of the seven taps (any may be None)."""
+    col, acts, pools, y6, y7, (B, H, W) = ctx
+    dev = col.device
+    c5 = pk.ch[-1][1]
+    n7, n6 = y7.shape[1], y6.shape[1]
+    g_pool_in = None  # gradient w.r.t. the (B,h5,w5,c5) input of the adaptive pool
+    hp, wp = pools[-1].shape[1], pools[-1].shape[2]
+    if g7 is not None or g8 is not None:
+        acc7 = None
+        if g8 is not None:
+            g8b = torch.zeros((B, pk.n8_pad), dtype=BF16, device=dev)
+            call("spyr_vec_epilogue", g8.contiguous().data_ptr(), None, None, None, 0, None, g8b.data_ptr(), pk.n8_pad, B,
+                 pk.n8)
+            acc7 = _fc_dgrad(g8b, pk.fc_w[2], B, pk.n8_pad, n7, dev)
+        if acc7 is None:
+            acc7 = g7.contiguous()
+            add7 = None
+        else:
+            add7 = g7.contiguous() if g7 is not None else None
+        g7b = torch.empty((B, n7), dtype=BF16, device=dev)
+        call("spyr_vec_epilogue", acc7.data_ptr(), None, add7.data_ptr() if add7 is not None else None, y7.data_ptr(), 2,
+             None, g7b.data_ptr(), n7, B, n7)
+        acc6 = _fc_dgrad(g7b, pk.fc_w[1], B, n7, n6, dev)
+        g6b = torch.empty((B, n6), dtype=BF16, device=dev)
+        call("spyr_vec_epilogue", acc6.data_ptr(), None, None, y6.data_ptr(), 2, None, g6b.data_ptr(), n6, B, n6)
+        accp = _fc_dgrad(g6b, pk.fc_w[0], B, n6, 49 * c5, dev)
+        g_pooled = ops.cast_bf16(accp).view(B, 7, 7, c5)
+        g_pool_in = torch.empty((B, hp, wp, c5), dtype=BF16, device=dev)
+        call("spyr_adaptive_avgpool_bwd", g_pooled.data_ptr(), g_pools[4].data_ptr() if g_pools[4] is not None else None,
+             g_pool_in.data_ptr(), B, hp, wp, 7, 7, c5)
+    else:
+        g_pool_in = g_pools[4]
+    if g_pool_in is None:
+        g_pool_in = torch.zeros((B, hp, wp, c5), dtype=BF16, device=dev)
+    # walk the conv stack backwards; g = gradient w.r.t. the output of the current stage
+    g = g_pool_in
+    level = 4
+    for j in range(len(pk.ch) - 1, -1, -1):
+        cin, cout = pk.ch[j]
+        a = acts[j]
+        h, w = a.shape[1], a.shape[2]
+        if j in POOL_AFTER:
+            # g is d/d(pool output): route to the arg-max and gate by the ReLU
+            g = ops.maxpool2_bwd(a, g, True)
+            level -= 1
+        if j == 0:
+            g_col, _ = ops.conv(B, h, w, 32, [Src(g, pk.w[0], cout, 1, mn=True)])
+            g_img = torch.empty((B, 3, h, w), dtype=F32, device=dev)
+            call("spyr_col2im3x3", g_col.data_ptr(), B, h, w, pk.invstd.data_ptr(), g_img.data_ptr(), 0)
+            return g_img
+        if (j - 1) in POOL_AFTER:
+            # the input of conv j is a pooled tap: add the tap's own gradient, no gate here
+            res = g_pools[level]
+            g, _ = ops.conv(B, h, w, cin, [Src(g, pk.w[j], cout, 3, mn=True)], residual=res)
+        else:
+            g, _ = ops.conv(B, h, w, cin, [Src(g, pk.w[j], cout, 3, mn=True)], dmask=acts[j - 1], dmask_slope=0.0)
+    raise AssertionError("unreachable")
