@@ -1,0 +1,246 @@
+"""Training / validation / inference driver, drop-in for the reference's `ModelWrapper` (model_wrapper.py:21-296).
+
+Same constructor keywords and `train(epochs, validate_after_n_iterations, device, save_model_after_n_epochs, w_rec,
+w_div)`, `validate()`, `inference(device)` entry points, same checkpoint dictionary and logged metric names.  The
+iteration body (`training_step`) issues the reference's five forwards in the reference's order (G, D(real), D(fake), G,
+D(fake)) but
+  * keeps every tensor on the device: the five logged scalars leave the GPU in ONE copy per iteration;
+  * does not compute what the reference computes and throws away (D weight gradients in the generator phase,
+    image / mask gradients of the real batch);
+  * replaces nn.DataParallel (main.py:91-94) by one process per GPU: pass `reducer=distributed.GradientReducer()`
+    and gradients are averaged over ranks with NCCL after each backward.
+"""
+import os
+from datetime import datetime
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import misc
+from .lossfunction import (DiversityLoss, LSGANDiscriminatorLoss, LSGANGeneratorLoss, SemanticReconstructionLoss)
+from .models import VGG16
+
+METRICS = ("loss_discriminator_real", "loss_discriminator_fake", "loss_generator",
+           "loss_generator_semantic_reconstruction", "loss_generator_diversity")
+
+
+def _unwrap(module):
+    return module.module if isinstance(module, nn.DataParallel) else module
+
+
+def _set_requires_grad(module, flag):
+    for p in module.parameters():
+        p.requires_grad_(flag)
+
+
+class ModelWrapper(object):
+    '''
+    Model wrapper implementing training, validation and inference of the whole adversarial architecture
+    '''
+
+    def __init__(self, generator, discriminator, training_dataset, validation_dataset, vgg16=None,
+                 generator_optimizer: torch.optim.Optimizer = None, discriminator_optimizer: torch.optim.Optimizer = None,
+                 generator_loss: nn.Module = None, discriminator_loss: nn.Module = None,
+                 semantic_reconstruction_loss: nn.Module = None, diversity_loss: nn.Module = None,
+                 save_data_path: str = 'saved_data', reducer=None, fid_function=None) -> None:
+        # nn.DataParallel wrappers are accepted for API compatibility and unwrapped: multi-GPU runs are one process per GPU
+        self.generator = _unwrap(generator)
+        self.discriminator = _unwrap(discriminator)
+        self.training_dataset = training_dataset
+        self.validation_dataset_fid = validation_dataset
+        self.vgg16 = _unwrap(vgg16) if vgg16 is not None else VGG16()
+        self.generator_optimizer = generator_optimizer
+        self.discriminator_optimizer = discriminator_optimizer
+        self.generator_loss = generator_loss or LSGANGeneratorLoss()
+        self.discriminator_loss = discriminator_loss or LSGANDiscriminatorLoss()
+        self.semantic_reconstruction_loss = semantic_reconstruction_loss or SemanticReconstructionLoss()
+        self.diversity_loss = diversity_loss or DiversityLoss()
+        self.latent_dimensions = self.generator.latent_dimensions
+        self.reducer = reducer
+        self.fid_function = fid_function
+        _set_requires_grad(self.vgg16, False)  # frozen encoder (model_wrapper.py:67-68)
+        self.logger = misc.Logger()
+        self.is_main_process = reducer is None or reducer.rank == 0
+        stamp = str(datetime.now())
+        self.path_save_models = os.path.join(save_data_path, 'models_' + stamp)
+        self.path_save_plots = os.path.join(save_data_path, 'plots_' + stamp)
+        self.path_save_metrics = os.path.join(save_data_path, 'metrics_' + stamp)
+        if self.is_main_process:
+            for path in (self.path_save_models, self.path_save_plots, self.path_save_metrics):
+                os.makedirs(path, exist_ok=True)
+        for name in ('generator', 'discriminator', 'vgg16', 'generator_optimizer', 'discriminator_optimizer',
+                     'generator_loss', 'discriminator_loss', 'diversity_loss', 'semantic_reconstruction_loss'):
+            self.logger.hyperparameter[name] = str(getattr(self, name))
+        self.progress_bar = None
+        self._images_seen = 0
+
+    # ------------------------------------------------------------------------------------------------
+    # one iteration of model_wrapper.py:136-190
+    # ------------------------------------------------------------------------------------------------
+    def training_step(self, images_real: torch.Tensor, labels: torch.Tensor, masks: List[torch.Tensor],
+                      w_rec: float = 0.1, w_div: float = 0.1, noise=None) -> Dict[str, torch.Tensor]:
+        """Runs the discriminator update then the generator update on one device-resident batch and returns the five
+        loss scalars as device tensors (no host synchronisation).  `noise` optionally supplies the two latent batches."""
+        G, D, V = self.generator, self.discriminator, self.vgg16
+        batch = images_real.shape[0]
+        device = images_real.device
+        class_float = labels.float()
+        z_d, z_g = noise if noise is not None else (None, None)
+        # ---- discriminator phase ----
+        G.zero_grad(set_to_none=True)
+        D.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            features_real = V(images_real)
+            if z_d is None:
+                z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
+            images_fake = G(input=z_d, features=features_real, masks=masks, class_id=class_float)
+        prediction_real = D(images_real, labels)
+        prediction_fake = D(images_fake, labels)
+        loss_d_real, loss_d_fake = self.discriminator_loss(prediction_real, prediction_fake)
+        (loss_d_real + loss_d_fake).backward()
+        if self.reducer is not None:
+            self.reducer.average(D)
+        self.discriminator_optimizer.step()
+        # ---- generator phase: D acts as a fixed critic, so its weight gradients are not requested ----
+        G.zero_grad(set_to_none=True)
+        D.zero_grad(set_to_none=True)
+        _set_requires_grad(D, False)
+        try:
+            if z_g is None:
+                z_g = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
+            images_fake = G(input=z_g, features=features_real, masks=masks, class_id=class_float)
+            prediction_fake = D(images_fake, labels)
+            loss_g = self.generator_loss(prediction_fake)
+            loss_div = w_div * self.diversity_loss(images_fake, z_g)
+            features_fake = V(images_fake)
+            loss_rec = w_rec * self.semantic_reconstruction_loss(features_real, features_fake, masks)
+            (loss_g + loss_rec + loss_div).backward()
+        finally:
+            _set_requires_grad(D, True)
+        if self.reducer is not None:
+            self.reducer.average(G)
+        self.generator_optimizer.step()
+        return {"loss_discriminator_real": loss_d_real.detach(), "loss_discriminator_fake": loss_d_fake.detach(),
+                "loss_generator": loss_g.detach(), "loss_generator_semantic_reconstruction": loss_rec.detach().reshape(()),
+                "loss_generator_diversity": loss_div.detach()}
+
+    def _to_device(self, images_real, labels, masks, device):
+        images_real = images_real.detach().to(device, non_blocking=True)
+        labels = labels.to(device, non_blocking=True)
+        masks = [m.detach().to(device, non_blocking=True) for m in masks]
+        return images_real, labels, masks
+
+    def train(self, epochs: int = 20, validate_after_n_iterations: int = 100000, device: str = 'cuda',
+              save_model_after_n_epochs: int = 1, w_rec: float = 0.1, w_div: float = 0.1) -> None:
+        """
+        Training loop (reference model_wrapper.py:93-228)
+        """
+        self.logger.hyperparameter['w_rec'] = str(w_rec)
+        self.logger.hyperparameter['w_div'] = str(w_div)
+        batch_size = self.training_dataset.batch_size
+        validate_after_n_iterations = max(1, validate_after_n_iterations // batch_size) * batch_size
+        self.generator.train()
+        self.discriminator.train()
+        self.vgg16.eval()
+        for module in (self.generator, self.discriminator, self.vgg16):
+            module.to(device)
+        total = epochs * len(self.training_dataset.dataset)
+        try:
+            from tqdm import tqdm
+            self.progress_bar = tqdm(total=total, dynamic_ncols=True, disable=not self.is_main_process)
+        except Exception:  # pragma: no cover
+            self.progress_bar = None
+        fid = float('nan')
+        if self.validation_dataset_fid is not None and self.fid_function is not None:
+            self.inference(device=device)
+            fid = self.validate()
+        for epoch in range(epochs):
+            self.generator.train()
+            self.discriminator.train()
+            self.vgg16.eval()
+            for images_real, labels, masks in self.training_dataset:
+                self._images_seen += images_real.shape[0]
+                if self.progress_bar is not None:
+                    self.progress_bar.update(n=images_real.shape[0])
+                images_real, labels, masks = self._to_device(images_real, labels, masks, device)
+                losses = self.training_step(images_real, labels, masks, w_rec=w_rec, w_div=w_div)
+                values = torch.stack([losses[name] for name in METRICS]).tolist()  # the only host sync of the iteration
+                if self.progress_bar is not None:
+                    self.progress_bar.set_description(
+                        'FID={:.4f}, Loss Div={:.4f}, Loss Rec={:.4f}, Loss G={:.4f}, Loss D={:.4f}'.format(
+                            fid, values[4], values[3], values[2], values[0] + values[1]))
+                for name, value in zip(METRICS, values):
+                    self.logger.log(metric_name=name, value=value)
+                self.logger.log(metric_name='iterations', value=self._images_seen)
+                self.logger.log(metric_name='epoch', value=epoch)
+                if self._images_seen % validate_after_n_iterations == 0 and self.fid_function is not None \
+                        and self.validation_dataset_fid is not None:
+                    fid = self.validate()
+                    self.inference(device=device)
+                    self.logger.log(metric_name='fid', value=fid)
+                    self.logger.log(metric_name='iterations_fid', value=self._images_seen)
+                    if self.is_main_process:
+                        self.logger.save_metrics(self.path_save_metrics)
+            if epoch % save_model_after_n_epochs == 0 and self.is_main_process:
+                self.save_checkpoint(os.path.join(self.path_save_models, 'checkpoint_{}.pt'.format(str(epoch).zfill(3))))
+            if self.validation_dataset_fid is not None:
+                self.inference(device=device)
+            if self.is_main_process:
+                self.logger.save_metrics(self.path_save_metrics)
+        if self.progress_bar is not None:
+            self.progress_bar.close()
+
+    def save_checkpoint(self, path: str) -> None:
+        """Same dictionary as reference model_wrapper.py:215-223 (state_dict keys are interchangeable)."""
+        torch.save({"generator": self.generator.state_dict(), "discriminator": self.discriminator.state_dict(),
+                    "generator_optimizer": self.generator_optimizer.state_dict(),
+                    "discriminator_optimizer": self.discriminator_optimizer.state_dict()}, path)
+
+    @torch.no_grad()
+    def validate(self) -> float:
+        '''
+        FID estimate through the user-supplied `fid_function(dataset_real=, generator=, vgg16=)` (the reference's
+        frechet_inception_distance needs a pretrained InceptionV3 download and is outside this package's scope)
+        '''
+        if self.fid_function is None:
+            raise RuntimeError("validate() needs ModelWrapper(..., fid_function=...): the FID of the reference depends "
+                               "on downloaded InceptionV3 weights (frechet_inception_distance.py:12-42)")
+        self.generator.eval()
+        self.vgg16.eval()
+        fid = self.fid_function(dataset_real=self.validation_dataset_fid, generator=self.generator, vgg16=self.vgg16)
+        self.generator.train()
+        return float(fid)
+
+    @torch.no_grad()
+    def inference(self, device: str = 'cuda') -> Optional[torch.Tensor]:
+        '''
+        7x7 grid: seven validation images (rows) generated from each of the seven pyramid levels (columns), as
+        reference model_wrapper.py:247-296 but one batched generator call per level instead of 49 single-image calls
+        '''
+        import numpy as np
+        self.generator.to(device)
+        self.vgg16.to(device)
+        self.generator.eval()
+        dataset = self.validation_dataset_fid.dataset
+        picks = np.random.choice(range(len(dataset)), replace=False, size=7)
+        samples = [dataset[int(i)] for i in picks]
+        images = torch.stack([s[0] for s in samples]).float().to(device)
+        labels = torch.stack([s[1] for s in samples]).to(device)
+        features = self.vgg16(images)
+        grid = torch.empty(7, 7, images.shape[1], images.shape[2], images.shape[3], dtype=torch.float32, device=device)
+        for level in range(7):
+            masks = [m.expand(7, *m.shape[1:]).contiguous()
+                     for m in misc.get_masks_for_inference(level, add_batch_size=True, device=device)]
+            z = torch.randn(7, self.latent_dimensions, dtype=torch.float32, device=device)
+            grid[:, level] = self.generator(input=z, features=features, masks=masks, class_id=labels.float())
+        fake_images = grid.reshape(49, *grid.shape[2:])
+        if self.is_main_process:
+            try:
+                import torchvision
+                torchvision.utils.save_image(misc.normalize_0_1_batch(fake_images), os.path.join(
+                    self.path_save_plots, 'predictions_{}.png'.format(self._images_seen)), nrow=7)
+            except Exception:  # pragma: no cover - plotting is best effort
+                pass
+        self.generator.train()
+        return fake_images

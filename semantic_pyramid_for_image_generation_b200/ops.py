@@ -14,6 +14,21 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 LRELU = 0.2
 
+# bench.py sets this to a list to time every tensor-core launch with CUDA events on the launching stream:
+# entries are (kernel, algorithmic_flops, algorithmic_bytes, start_event, end_event)
+PROFILE = None
+
+
+def _profiled(kernel, flops, nbytes, name, desc):
+    if PROFILE is None:
+        call(name, desc)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, desc)
+    e1.record()
+    PROFILE.append((kernel, flops, nbytes, e0, e1))
+
 
 def empty_bf16(*shape, device=None):
     return torch.empty(shape, dtype=BF16, device=device or "cuda")
@@ -65,7 +80,14 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
             y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
             d.y_act = y_act.data_ptr()
         d.act, d.act_slope = act, act_slope
-    call("spyr_conv2d_fprop", C.byref(d))
+    if PROFILE is None:
+        call("spyr_conv2d_fprop", C.byref(d))
+    else:
+        kred = sum(s.cin * s.ksize * s.ksize for s in srcs)
+        npx = B * H * W
+        nbytes = 2 * npx * sum(s.cin for s in srcs) + 2 * Cout * kred + (4 if f32_out is not None else 2) * npx * Cout * (
+            int(want_raw) + int(want_act) if f32_out is None else 1)
+        _profiled("conv_fprop_kernel", 2.0 * npx * Cout * kred, float(nbytes), "spyr_conv2d_fprop", C.byref(d))
     return y_raw, y_act
 
 
@@ -75,7 +97,12 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
     d.B, d.H, d.W, d.Cin, d.Cout, d.ksize = B, H, W, Cin, Cout, ksize
     d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw_ptr
     d.cin_stride, d.per_image = cin_stride, int(per_image)
-    call("spyr_conv2d_wgrad", C.byref(d))
+    if PROFILE is None:
+        call("spyr_conv2d_wgrad", C.byref(d))
+    else:
+        npx = B * H * W
+        _profiled("conv_wgrad_kernel", 2.0 * npx * Cin * Cout * ksize * ksize,
+                  float(2 * npx * (Cin + Cout) + 4 * Cin * Cout * ksize * ksize), "spyr_conv2d_wgrad", C.byref(d))
 
 
 def colsum(g, C_, out0, out1=None, out2=None):
