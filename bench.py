@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--dump-profile", default=None, help="write the per-launch tensor-kernel timings of one step here")
     return ap.parse_args()
 
 
@@ -290,7 +291,17 @@ def main():
     prof = ops.PROFILE
     ops.PROFILE = None
     agg = {}
-    for kernel, flops, nbytes, a, b in prof:
+    if args.dump_profile and rank == 0:
+        rows = {}
+        for kernel, flops, nbytes, a, b, label in prof:
+            r = rows.setdefault((kernel, label), [0, 0.0, flops, nbytes])
+            r[0] += 1
+            r[1] += a.elapsed_time(b)
+        with open(args.dump_profile, "w") as f:
+            for (kernel, label), (n, ms, flops, nbytes) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                f.write("%-18s %-46s n=%3d total %8.3f ms  avg %7.1f us  %7.1f TFLOP/s  %6.0f GB/s(alg)\n" % (
+                    kernel, label, n, ms, ms / n * 1e3, flops * n / (ms * 1e-3) / 1e12, nbytes * n / (ms * 1e-3) / 1e9))
+    for kernel, flops, nbytes, a, b, _label in prof:
         rec = agg.setdefault(kernel, [0.0, 0.0, 0.0, 0])
         rec[0] += flops
         rec[1] += nbytes

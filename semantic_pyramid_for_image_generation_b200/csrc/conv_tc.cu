@@ -15,9 +15,11 @@
 // Replaces the cuDNN/MKL-DNN calls behind nn.Conv2d at reference models.py:34,55-60,232-243,299-315,
 // 393-404,438-449 and torchvision VGG features/classifier (models.py:201-211).
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/spyramid_b200.h"
 
 extern void spyr_count_launch();
+int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream);
 
 namespace {
 
@@ -450,29 +452,29 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         }
       }
     } else if (warp == 1) {
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = k_begin; it < k_end; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
+      // one thread issues every MMA; descriptors advance by integer adds on the start-address field (16-byte units)
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, 1, 1);
+        const uint64_t hi = ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)((p.lbo >> 4) & 0x3FFF) << 16) |
+                            ((uint64_t)((p.sbo >> 4) & 0x3FFF) << 32);
+        const uint32_t base16 = (smem_u32(smem) & 0x3FFFF) >> 4;
+        const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a16 = (uint32_t)a_bytes >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da0 = hi | (uint64_t)(base16 + (uint32_t)stage * stage16);
+          const uint64_t db0 = da0 + a16;
 #pragma unroll
-          for (int k = 0; k < KP / 16; ++k) {
-            // 16 pixels (K) per MMA = 16 rows of 128 B = 2 swizzle atoms
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 2048, p.lbo, p.sbo);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 2048, p.lbo, p.sbo);
-            umma_bf16(tmem_base, da, db, idesc, (it > k_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < KP / 16; ++k)  // 16 pixels (K) per MMA = 16 rows of 128 B = 2 KB
+            umma_bf16(tmem_base, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc, (it > k_begin || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (it == k_end - 1) umma_commit(tmem_full_bar);
-        }
-        __syncwarp();
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     } else if (warp >= 4) {
@@ -532,6 +534,15 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   SPYR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 3, "conv2d_fprop: nsrc=%d out of range", d->nsrc);
   SPYR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "conv2d_fprop: bad shape");
   SPYR_REQUIRE(is_pow2(d->H) && is_pow2(d->W) || (d->H == 1 && d->W == 1), "conv2d_fprop: H,W must be powers of two");
+  {
+    // maps of 16x8 pixels and larger run on the persistent halo-tiled kernel (conv_halo.cu); SPYR_CONV_LEGACY=1 forces
+    // the per-tap kernel below (A/B measurements)
+    static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
+    if (!legacy) {
+      const int rc = spyr_conv_halo_launch(d, stream);
+      if (rc >= 0) return rc;
+    }
+  }
   FpropParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;

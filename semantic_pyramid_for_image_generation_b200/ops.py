@@ -19,7 +19,7 @@ LRELU = 0.2
 PROFILE = None
 
 
-def _profiled(kernel, flops, nbytes, name, desc):
+def _profiled(kernel, flops, nbytes, name, desc, label=""):
     if PROFILE is None:
         call(name, desc)
         return
@@ -27,7 +27,7 @@ def _profiled(kernel, flops, nbytes, name, desc):
     e0.record()
     call(name, desc)
     e1.record()
-    PROFILE.append((kernel, flops, nbytes, e0, e1))
+    PROFILE.append((kernel, flops, nbytes, e0, e1, label))
 
 
 def empty_bf16(*shape, device=None):
@@ -87,7 +87,9 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         npx = B * H * W
         nbytes = 2 * npx * sum(s.cin for s in srcs) + 2 * Cout * kred + (4 if f32_out is not None else 2) * npx * Cout * (
             int(want_raw) + int(want_act) if f32_out is None else 1)
-        _profiled("conv_fprop_kernel", 2.0 * npx * Cout * kred, float(nbytes), "spyr_conv2d_fprop", C.byref(d))
+        label = "B%d %dx%d Cout=%d %s" % (B, H, W, Cout, "+".join(
+            "%dk%d%s%s" % (s.cin, s.ksize, "T" if s.mn else "", "b" if s.per_image else "") for s in srcs))
+        _profiled("conv_fprop_kernel", 2.0 * npx * Cout * kred, float(nbytes), "spyr_conv2d_fprop", C.byref(d), label)
     return y_raw, y_act
 
 
@@ -102,7 +104,8 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
     else:
         npx = B * H * W
         _profiled("conv_wgrad_kernel", 2.0 * npx * Cin * Cout * ksize * ksize,
-                  float(2 * npx * (Cin + Cout) + 4 * Cin * Cout * ksize * ksize), "spyr_conv2d_wgrad", C.byref(d))
+                  float(2 * npx * (Cin + Cout) + 4 * Cin * Cout * ksize * ksize), "spyr_conv2d_wgrad", C.byref(d),
+                  "B%d %dx%d Cin=%d Cout=%d k%d%s" % (B, H, W, Cin, Cout, ksize, "b" if per_image else ""))
 
 
 def colsum(g, C_, out0, out1=None, out2=None):

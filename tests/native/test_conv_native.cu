@@ -340,6 +340,31 @@ static int test_wgrad_per_image(int B, int H, int W, int Cin, int Cout) {
   return ok ? 0 : 1;
 }
 
+extern "C" int spyr_dbg_halo_probe(const void* x, const void* w, float* y, int B, int H, int W, int C, int Cout,
+                                   int base_off_mode, void* stream);
+static int test_halo(int B, int H, int W, int C, int Cout, int mode) {
+  std::vector<float> x((size_t)B * H * W * C), w((size_t)9 * Cout * C);
+  for (auto& v : x) v = bf16_round(frand());
+  for (auto& v : w) v = bf16_round(frand() * 0.05f);
+  std::vector<float> ref((size_t)B * H * W * Cout, 0.f);
+  ref_conv(x, w, B, H, W, C, Cout, 3, ref);
+  Dev dx, dw, dy;
+  auto xb = to_bf16(x); auto wb = to_bf16(w);
+  dx.alloc(xb.size() * 2); dw.alloc(wb.size() * 2); dy.alloc(ref.size() * 4);
+  CK(cudaMemcpy(dx.p, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  int rc = spyr_dbg_halo_probe(dx.p, dw.p, (float*)dy.p, B, H, W, C, Cout, mode, 0);
+  if (rc) { printf("  halo rc=%d: %s\n", rc, spyr_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  halo kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
+  std::vector<float> got(ref.size());
+  CK(cudaMemcpy(got.data(), dy.p, ref.size() * 4, cudaMemcpyDeviceToHost));
+  const double err = rel_l2(got, ref);
+  const bool ok = err < 1e-5;
+  printf("%s halo B=%d %dx%d C=%d Cout=%d base_off_mode=%d relL2=%.3e\n", ok ? "PASS" : "FAIL", B, H, W, C, Cout, mode, err);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int fails = 0;
   const char* mode = argc > 1 ? argv[1] : "all";
@@ -382,6 +407,12 @@ int main(int argc, char** argv) {
     fails += test_wgrad_per_image(3, 32, 32, 256, 32);  // dK
     fails += test_wgrad_per_image(3, 32, 32, 256, 128); // dV
     fails += test_wgrad_per_image(2, 16, 16, 64, 16);
+  }
+  if (!strcmp(mode, "halo")) {
+    for (int m = 0; m < 2; ++m) {
+      fails += test_halo(2, 16, 16, 64, 64, m);
+      fails += test_halo(1, 32, 16, 128, 32, m);
+    }
   }
   printf("native conv tests: %d failure(s)\n", fails);
   return fails ? 1 : 0;
