@@ -204,29 +204,20 @@ def main():
         losses = eager_step()
     torch.cuda.synchronize()
 
-    # ---- CUDA graph of the whole step (single GPU); multi-GPU steps stay eager around the NCCL calls ----
-    graph = None
+    # ---- the iteration as CUDA graphs (three graphs, the two NCCL gradient averages run between them) ----
+    captured = None
     graph_note = "eager"
     launches_per_step = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                eager_step()
-            torch.cuda.current_stream().wait_stream(side)
+            captured = wrapper.capture_training_step(s_images, s_labels, s_masks)
+            launches_per_step = captured.launches_per_step
+            losses = captured()
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            _native.launch_count_reset()
-            with torch.cuda.graph(graph):
-                losses = eager_step()
-            launches_per_step = _native.launch_count()
-            graph.replay()
-            torch.cuda.synchronize()
-            graph_note = "cuda-graph"
+            graph_note = "cuda-graphs (3 per step)"
         except Exception as exc:  # noqa: BLE001
-            graph = None
-            graph_note = "eager (graph capture failed: %s)" % str(exc)[:120]
+            captured = None
+            graph_note = "eager (graph capture failed: %s)" % str(exc)[:160]
             torch.cuda.synchronize()
     if launches_per_step is None:
         _native.launch_count_reset()
@@ -235,8 +226,8 @@ def main():
         launches_per_step = _native.launch_count()
 
     def step():
-        if graph is not None:
-            graph.replay()
+        if captured is not None:
+            captured()
         else:
             eager_step()
 
@@ -270,11 +261,7 @@ def main():
         s_labels.copy_(h_labels, non_blocking=True)
         for dm, hm in zip(s_masks, h_masks):
             dm.copy_(hm, non_blocking=True)
-        if graph is not None:
-            graph.replay()
-            out = losses
-        else:
-            out = eager_step()
+        out = captured() if captured is not None else eager_step()
         loss_host.copy_(torch.stack([out[name] for name in METRICS]), non_blocking=True)
     t1.record()
     torch.cuda.synchronize()

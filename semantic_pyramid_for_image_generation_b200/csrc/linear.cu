@@ -73,12 +73,15 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
 }
 
 // gx[b][k] = (sum_o gy'[b][o] W[o][k]) * inv_sigma * f'(x[b][k]),  gy' = gy * out_lrelu'(y)
+// CTA = 32 k-columns x 8 slices of the output dimension (one warp per slice), reduced through shared memory.
 __global__ void linear_bwd_x_kernel(const float* __restrict__ gy, const float* __restrict__ y, float out_slope,
                                     const float* __restrict__ w, const float* __restrict__ sigma,
                                     const float* __restrict__ x, float in_slope, float* __restrict__ gx, int accumulate,
                                     int B, int K, int O) {
   __shared__ float gs[LB][256];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[8][LB][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
   const int b0 = blockIdx.y * LB;
   float acc[LB];
 #pragma unroll
@@ -97,22 +100,30 @@ __global__ void linear_bwd_x_kernel(const float* __restrict__ gy, const float* _
     __syncthreads();
     if (k < K) {
       const int no = min(256, O - o0);
-      for (int oo = 0; oo < no; ++oo) {
-        const float wv = w[(size_t)(o0 + oo) * K + k];
+#pragma unroll 4
+      for (int oo = ty; oo < no; oo += 8) {
+        const float wv = __ldg(&w[(size_t)(o0 + oo) * K + k]);
 #pragma unroll
         for (int b = 0; b < LB; ++b) acc[b] += wv * gs[b][oo];
       }
     }
   }
-  if (k >= K) return;
-  const float inv = sigma != nullptr ? 1.f / __ldg(sigma) : 1.f;
 #pragma unroll
-  for (int b = 0; b < LB; ++b) {
-    if (b0 + b >= B) break;
-    float v = acc[b] * inv;
-    const size_t i = (size_t)(b0 + b) * K + k;
-    if (x != nullptr && !(x[i] > 0.f)) v *= in_slope;
-    gx[i] = accumulate ? gx[i] + v : v;
+  for (int b = 0; b < LB; ++b) part[ty][b][tx] = acc[b];
+  __syncthreads();
+  if (ty == 0 && k < K) {
+    const float inv = sigma != nullptr ? 1.f / __ldg(sigma) : 1.f;
+#pragma unroll
+    for (int b = 0; b < LB; ++b) {
+      if (b0 + b >= B) break;
+      float v = 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) v += part[s][b][tx];
+      v *= inv;
+      const size_t i = (size_t)(b0 + b) * K + k;
+      if (x != nullptr && !(x[i] > 0.f)) v *= in_slope;
+      gx[i] = accumulate ? gx[i] + v : v;
+    }
   }
 }
 
@@ -152,27 +163,33 @@ __global__ void dhead_out_fwd_kernel(const float* __restrict__ cls, const float*
   }
 }
 // g_cls[j] = sum_{i,k} g[i,j,k];  g_feat[j,k] = sum_i g[i,j,k] emb[i,k];  g_embw[idx[i]][k] += sum_j g[i,j,k] feat[j,k]
+// one CTA per batch row r (it plays j for g_cls / g_feat and i for g_embw), threads over k
 __global__ void dhead_out_bwd_kernel(const float* __restrict__ g, const float* __restrict__ feat,
                                      const float* __restrict__ emb_w, const float* __restrict__ sigma,
                                      const int* __restrict__ idx, float* __restrict__ g_cls, float* __restrict__ g_feat,
                                      float* __restrict__ g_embw, int B, int E) {
+  __shared__ float red[32];
   const float inv = 1.f / __ldg(sigma);
-  // one block; threads over (row, k)
-  for (int t = threadIdx.x; t < B * E; t += blockDim.x) {
-    const int r = t / E, k = t % E;
+  const int r = blockIdx.x;
+  float cls_acc = 0.f;
+  for (int k = threadIdx.x; k < E; k += blockDim.x) {
     float gf = 0.f, ge = 0.f;
     for (int q = 0; q < B; ++q) {
-      gf += g[((size_t)q * B + r) * E + k] * emb_w[(size_t)idx[q] * E + k] * inv;  // r plays j, q plays i
-      ge += g[((size_t)r * B + q) * E + k] * feat[(size_t)q * E + k];              // r plays i, q plays j
+      const float gj = g[((size_t)q * B + r) * E + k];  // i = q, j = r
+      gf += gj * emb_w[(size_t)idx[q] * E + k] * inv;
+      cls_acc += gj;
+      ge += g[((size_t)r * B + q) * E + k] * feat[(size_t)q * E + k];  // i = r, j = q
     }
-    g_feat[t] = gf;
+    g_feat[(size_t)r * E + k] = gf;
     if (g_embw != nullptr) atomicAdd(g_embw + (size_t)idx[r] * E + k, ge);
   }
-  for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < B; ++i)
-      for (int k = 0; k < E; ++k) s += g[((size_t)i * B + j) * E + k];
-    g_cls[j] = s;
+  cls_acc = warp_sum(cls_acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cls_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    g_cls[r] = t;
   }
 }
 
@@ -192,8 +209,8 @@ extern "C" int spyr_linear_bwd_x(const float* gy, const float* y, float out_slop
                                  const float* x, float in_slope, float* gx, int accumulate, int B, int K, int O,
                                  void* stream) {
   SPYR_REQUIRE(gy && w && gx, "linear_bwd_x: bad arguments");
-  dim3 grid(ceil_div(K, 128), ceil_div(B, LB));
-  linear_bwd_x_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gy, y, out_slope, w, sigma, x, in_slope, gx, accumulate, B, K,
+  dim3 grid(ceil_div(K, 32), ceil_div(B, LB));
+  linear_bwd_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, y, out_slope, w, sigma, x, in_slope, gx, accumulate, B, K,
                                                               O);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -218,7 +235,7 @@ extern "C" int spyr_dhead_out_fwd(const float* cls, const float* feat, const flo
 }
 extern "C" int spyr_dhead_out_bwd(const float* g, const float* feat, const float* emb_w, const float* sigma, const int* idx,
                                   float* g_cls, float* g_feat, float* g_embw, int B, int E, void* stream) {
-  dhead_out_bwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(g, feat, emb_w, sigma, idx, g_cls, g_feat, g_embw, B, E);
+  dhead_out_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(g, feat, emb_w, sigma, idx, g_cls, g_feat, g_embw, B, E);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -65,7 +65,7 @@ __global__ void sn_wtu_kernel(const spyr_sn_layer* __restrict__ tab, int n, floa
   atomicAdd(scratch + L.scratch_off + j, acc);
 }
 
-constexpr int WV_ROWS = 32;
+constexpr int WV_ROWS = 8;  // one weight row per warp
 
 // s[i] = sum_j W[i][j] v[j], v = t / max(|t|, eps) (train) or the stored v (eval); one CTA also stores v
 __global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch, int training,
@@ -75,7 +75,6 @@ __global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float
   const int l = find_layer(tab, n, blockIdx.x, 1, &sh_idx);
   const spyr_sn_layer L = tab[l];
   const int tile = blockIdx.x - L.tile0_wv;
-  const int r0 = tile * WV_ROWS;
   const float* vec;
   float vscale = 1.f;
   if (training) {
@@ -91,16 +90,30 @@ __global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float
     vec = L.v;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_per_warp = WV_ROWS / (blockDim.x >> 5);
-  for (int rr = 0; rr < rows_per_warp; ++rr) {
-    const int i = r0 + warp * rows_per_warp + rr;
-    if (i >= L.rows) break;
-    const float* wp = L.w + (size_t)i * L.cols;
-    float acc = 0.f;
+  const int i = tile * WV_ROWS + warp;
+  if (i >= L.rows) return;
+  const float* wp = L.w + (size_t)i * L.cols;
+  float acc = 0.f;
+  if ((L.cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(vec)) & 15) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(wp);
+    const float4* v4 = reinterpret_cast<const float4*>(vec);
+    const int n4 = L.cols >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < n4; j += 32) {
+      const float4 a = __ldg(w4 + j), b = v4[j];
+      a0 += a.x * b.x;
+      a1 += a.y * b.y;
+      a2 += a.z * b.z;
+      a3 += a.w * b.w;
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+#pragma unroll 4
     for (int j = lane; j < L.cols; j += 32) acc += wp[j] * vec[j];
-    acc = warp_sum(acc) * vscale;
-    if (lane == 0) scratch[L.scratch_off + L.cols + i] = acc;
   }
+  acc = warp_sum(acc) * vscale;
+  if (lane == 0) scratch[L.scratch_off + L.cols + i] = acc;
 }
 
 // sigma, u update, saved copies, BF16 pack.  One CTA per weight row (pack layers) or one CTA per layer.
@@ -250,8 +263,8 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     t_pack += L.pack_cin > 0 ? L.rows : 1;
     L.tile0_bwd = t_bwd;
     t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, BT);
-    L.scratch_off = scratch;
-    scratch += L.cols + L.rows;
+    L.scratch_off = scratch;  // 16-byte aligned so the power-iteration vector can be read as float4
+    scratch += (L.cols + L.rows + 3) & ~3;
     L.saved_off = saved;
     saved += 1 + L.rows + L.cols;
   }

@@ -78,38 +78,36 @@ class ModelWrapper(object):
     # ------------------------------------------------------------------------------------------------
     # one iteration of model_wrapper.py:136-190
     # ------------------------------------------------------------------------------------------------
-    def training_step(self, images_real: torch.Tensor, labels: torch.Tensor, masks: List[torch.Tensor],
-                      w_rec: float = 0.1, w_div: float = 0.1, noise=None) -> Dict[str, torch.Tensor]:
-        """Runs the discriminator update then the generator update on one device-resident batch and returns the five
-        loss scalars as device tensors (no host synchronisation).  `noise` optionally supplies the two latent batches."""
+    def _phase_discriminator(self, images_real, labels, masks, z_d):
+        """VGG(real), G (no grad), D(real), D(fake), LSGAN loss, backward.  Leaves D's gradients in D's flat arena."""
         G, D, V = self.generator, self.discriminator, self.vgg16
-        batch = images_real.shape[0]
-        device = images_real.device
-        class_float = labels.float()
-        z_d, z_g = noise if noise is not None else (None, None)
-        # ---- discriminator phase ----
+        batch, device = images_real.shape[0], images_real.device
         G.zero_grad(set_to_none=True)
         D.zero_grad(set_to_none=True)
         with torch.no_grad():
             features_real = V(images_real)
             if z_d is None:
                 z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
-            images_fake = G(input=z_d, features=features_real, masks=masks, class_id=class_float)
+            images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
         prediction_real = D(images_real, labels)
         prediction_fake = D(images_fake, labels)
         loss_d_real, loss_d_fake = self.discriminator_loss(prediction_real, prediction_fake)
         (loss_d_real + loss_d_fake).backward()
-        if self.reducer is not None:
-            self.reducer.average(D)
+        return features_real, loss_d_real.detach(), loss_d_fake.detach()
+
+    def _phase_generator(self, features_real, labels, masks, z_g, w_rec, w_div):
+        """D's Adam step, then G, D(fake), the three generator losses, backward.  D acts as a fixed critic here, so its
+        weight gradients are not requested (the reference computes and discards them)."""
+        G, D, V = self.generator, self.discriminator, self.vgg16
+        batch, device = labels.shape[0], labels.device
         self.discriminator_optimizer.step()
-        # ---- generator phase: D acts as a fixed critic, so its weight gradients are not requested ----
         G.zero_grad(set_to_none=True)
         D.zero_grad(set_to_none=True)
         _set_requires_grad(D, False)
         try:
             if z_g is None:
                 z_g = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
-            images_fake = G(input=z_g, features=features_real, masks=masks, class_id=class_float)
+            images_fake = G(input=z_g, features=features_real, masks=masks, class_id=labels.float())
             prediction_fake = D(images_fake, labels)
             loss_g = self.generator_loss(prediction_fake)
             loss_div = w_div * self.diversity_loss(images_fake, z_g)
@@ -118,12 +116,26 @@ class ModelWrapper(object):
             (loss_g + loss_rec + loss_div).backward()
         finally:
             _set_requires_grad(D, True)
+        return loss_g.detach(), loss_rec.detach().reshape(()), loss_div.detach()
+
+    def training_step(self, images_real: torch.Tensor, labels: torch.Tensor, masks: List[torch.Tensor],
+                      w_rec: float = 0.1, w_div: float = 0.1, noise=None) -> Dict[str, torch.Tensor]:
+        """Runs the discriminator update then the generator update on one device-resident batch and returns the five
+        loss scalars as device tensors (no host synchronisation).  `noise` optionally supplies the two latent batches."""
+        z_d, z_g = noise if noise is not None else (None, None)
+        features_real, loss_d_real, loss_d_fake = self._phase_discriminator(images_real, labels, masks, z_d)
         if self.reducer is not None:
-            self.reducer.average(G)
+            self.reducer.average(self.discriminator)
+        loss_g, loss_rec, loss_div = self._phase_generator(features_real, labels, masks, z_g, w_rec, w_div)
+        if self.reducer is not None:
+            self.reducer.average(self.generator)
         self.generator_optimizer.step()
-        return {"loss_discriminator_real": loss_d_real.detach(), "loss_discriminator_fake": loss_d_fake.detach(),
-                "loss_generator": loss_g.detach(), "loss_generator_semantic_reconstruction": loss_rec.detach().reshape(()),
-                "loss_generator_diversity": loss_div.detach()}
+        return {"loss_discriminator_real": loss_d_real, "loss_discriminator_fake": loss_d_fake, "loss_generator": loss_g,
+                "loss_generator_semantic_reconstruction": loss_rec, "loss_generator_diversity": loss_div}
+
+    def capture_training_step(self, images_real, labels, masks, w_rec: float = 0.1, w_div: float = 0.1):
+        """Returns a `CapturedTrainingStep`: the iteration recorded as CUDA graphs over the given (static) input tensors."""
+        return CapturedTrainingStep(self, images_real, labels, masks, w_rec, w_div)
 
     def _to_device(self, images_real, labels, masks, device):
         images_real = images_real.detach().to(device, non_blocking=True)
@@ -244,3 +256,60 @@ class ModelWrapper(object):
                 pass
         self.generator.train()
         return fake_images
+
+
+class CapturedTrainingStep(object):
+    """One training iteration as three CUDA graphs with the two gradient all-reduces between them:
+
+        graph A  discriminator phase (forward x4, backward)          -> NCCL average of D's gradient arena
+        graph B  D Adam step + generator phase (forward x3, backward) -> NCCL average of G's gradient arena
+        graph C  G Adam step
+
+    All kernels of the step are launched through the C-ABI on the capturing stream and nothing synchronises, so the
+    ~700 launches of an iteration cost three graph launches.  Inputs are read from the tensors given at capture time:
+    copy new batches into them (`load`) and call the object.  Single-process runs skip the collectives."""
+
+    def __init__(self, wrapper, images_real, labels, masks, w_rec=0.1, w_div=0.1):
+        self.w = wrapper
+        self.images, self.labels, self.masks = images_real, labels, list(masks)
+        # warm-up on a side stream (allocator, lazy tables, optimizer state), as CUDA-graph capture requires
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                wrapper.training_step(self.images, self.labels, self.masks, w_rec=w_rec, w_div=w_div)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _native
+        self.graph_a, self.graph_b, self.graph_c = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        _native.launch_count_reset()
+        with torch.cuda.graph(self.graph_a, pool=pool):
+            self.features_real, l_real, l_fake = wrapper._phase_discriminator(self.images, self.labels, self.masks, None)
+        self.d_arena = wrapper.discriminator._last_grad_arena
+        with torch.cuda.graph(self.graph_b, pool=pool):
+            l_g, l_rec, l_div = wrapper._phase_generator(self.features_real, self.labels, self.masks, None, w_rec, w_div)
+        self.g_arena = wrapper.generator._last_grad_arena
+        with torch.cuda.graph(self.graph_c, pool=pool):
+            wrapper.generator_optimizer.step()
+        self.launches_per_step = _native.launch_count()
+        self.losses = {"loss_discriminator_real": l_real, "loss_discriminator_fake": l_fake, "loss_generator": l_g,
+                       "loss_generator_semantic_reconstruction": l_rec, "loss_generator_diversity": l_div}
+
+    def load(self, images_real, labels, masks) -> None:
+        """Asynchronous copy of a new batch (pinned host or device tensors) into the captured input buffers."""
+        self.images.copy_(images_real, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        for dst, src in zip(self.masks, masks):
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self) -> Dict[str, torch.Tensor]:
+        red = self.w.reducer
+        self.graph_a.replay()
+        if red is not None and red.active:
+            red.average_flat(self.d_arena)
+        self.graph_b.replay()
+        if red is not None and red.active:
+            red.average_flat(self.g_arena)
+        self.graph_c.replay()
+        return self.losses

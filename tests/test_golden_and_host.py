@@ -174,7 +174,7 @@ def test_gradient_arena_and_spectral_norm_plan():
         tab[i].pack_cin = cin if taps == 9 else 0
     plan = N.SnPlan()
     N.call_nostream("spyr_sn_plan", tab, 2, C.byref(plan))
-    assert plan.tiles_wtu == 1 * 3 + 6 * 1 and plan.tiles_wv == 2 + 12 and plan.tiles_pack == 64 + 1
+    assert plan.tiles_wtu == 1 * 3 + 6 * 1 and plan.tiles_wv == 8 + 46 and plan.tiles_pack == 64 + 1
     assert plan.saved_floats == (1 + 64 + 576) + (1 + 365 + 128)
     tab[0].cols = 7  # inconsistent shape -> error status + message, no crash
     with pytest.raises(RuntimeError, match="bad shape"):
