@@ -20,6 +20,7 @@
 
 extern void spyr_count_launch();
 int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream);
+int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream);
 
 namespace {
 
@@ -494,9 +495,17 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         if (!valid) continue;
         const int col0 = n_off + c0;
         float* dst = dw_out + ((size_t)tap * p.cin_stride + ci) * p.Cout + col0;
+        if (col0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + j),
+                      make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                  __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -650,6 +659,14 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
   SPYR_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv2d_wgrad: ksize must be 1 or 3");
   SPYR_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "conv2d_wgrad: Cin/Cout must be multiples of 8");
   SPYR_REQUIRE((is_pow2(d->H) && is_pow2(d->W)) || (d->H == 1 && d->W == 1), "conv2d_wgrad: H,W must be powers of two");
+  {
+    // 3x3 gradients on maps of 16x8 pixels and larger run on the halo-tiled kernel (wgrad_halo.cu)
+    static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
+    if (!legacy) {
+      const int rc = spyr_wgrad_halo_launch(d, stream);
+      if (rc >= 0) return rc;
+    }
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;

@@ -101,8 +101,8 @@ class SNSet(object):
                 sten += 10 * s.rows
             else:
                 s.stencil_off = -1
-            s.gw_off = gw
-            gw += s.rows * s.cols
+            s.gw_off = gw  # 16-byte aligned slices: the wgrad kernels reduce with float4 atomics
+            gw += (s.rows * s.cols + 3) // 4 * 4
         self.pack_elems, self.stencil_floats, self.gw_floats = pack, sten, gw
         self._ptr_sig = None
         self.host_tab = None

@@ -390,6 +390,13 @@ int main(int argc, char** argv) {
     fails += test_wgrad(2, 32, 32, 256, 32, 1, 0, 0, 0);
     fails += test_wgrad(2, 64, 64, 64, 64, 3, 0, 0, 0);
     fails += test_wgrad(20, 1, 1, 512, 128, 1, 0, 0, 0);
+    // halo-tiled kernel: 64-channel inputs pair taps, 128-channel blocks pair chunks; ragged Cout; several splits
+    fails += test_wgrad(2, 16, 16, 64, 64, 3, 0, 0, 3);
+    fails += test_wgrad(1, 32, 32, 128, 128, 3, 0, 0, 0);
+    fails += test_wgrad(2, 32, 16, 256, 64, 3, 0, 0, 0);
+    fails += test_wgrad(2, 16, 16, 128, 256, 3, 0, 0, 1);
+    fails += test_wgrad(2, 16, 16, 64, 24, 3, 0, 0, 0);
+    fails += test_wgrad(1, 64, 64, 384, 128, 3, 0, 0, 0);
   }
   if (!strcmp(mode, "all") || !strcmp(mode, "dgrad")) {
     fails += test_dgrad(2, 16, 16, 64, 64, 3, false);

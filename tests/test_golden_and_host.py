@@ -158,7 +158,7 @@ def test_gradient_arena_and_spectral_norm_plan():
     ga, sn = d._ga, d._sn
     offs = sorted(ga.offsets.values())
     assert offs[0] == 0 and all(o % 64 == 0 for o in offs) and ga.total >= 16820994
-    assert sn.n == 28 and sn.gw_floats == sum(s.rows * s.cols for s in sn.specs)
+    assert sn.n == 28 and sn.gw_floats == sum((s.rows * s.cols + 3) // 4 * 4 for s in sn.specs)
     # first-layer operands are im2col rows; every other conv is [taps][cout][cin]
     assert sn.by_key["layers.0.main_block.0"].pack_mode == 1 and sn.by_key["layers.0.main_block.0"].pack_cin == 32
     assert sn.by_key["layers.0.residual_mapping"].pack_cin == 8
