@@ -75,6 +75,10 @@ typedef struct {
 } spyr_conv_desc;
 
 int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream);
+/* Fused tail of a split-K run: applies the epilogue fields of `d` (biases, stencil, gate, residual, y_raw / y_act) to the
+ * FP32 accumulator `acc` [B*H*W][Cout] that spyr_conv2d_fprop(y_f32 = acc, splits > 1) produced.  Used for the 4x4 / 8x8
+ * maps, where 3..30 output tiles cannot fill 148 SMs and the reduction dimension is split instead. */
+int spyr_conv2d_epilogue(const spyr_conv_desc* d, const float* acc, void* stream);
 
 /* Weight gradient of the same convolutions (torch autograd conv backward-weight at the call sites above):
  *   dw[tap][ci][co] += sum_{b,h,w} x[b,h+dy,w+dx,ci] * dy[b,h,w,co]     (fp32 red.add; caller zero-fills)

@@ -58,6 +58,7 @@ class AdamChunk(C.Structure):
 P = c_void_p
 _SIGNATURES = {
     "spyr_conv2d_fprop": [C.POINTER(ConvDesc), P],
+    "spyr_conv2d_epilogue": [C.POINTER(ConvDesc), P, P],
     "spyr_conv2d_wgrad": [C.POINTER(WgradDesc), P],
     "spyr_im2col3x3": [P, c_int, c_int, c_int, P, P, P, P],
     "spyr_col2im3x3": [P, c_int, c_int, c_int, P, P, c_int, P],

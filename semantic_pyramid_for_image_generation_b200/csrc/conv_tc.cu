@@ -251,9 +251,17 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
             }
             continue;
           }
+          if (col0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + j),
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
+          }
           continue;
         }
 #pragma unroll

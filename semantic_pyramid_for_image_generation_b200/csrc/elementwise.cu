@@ -554,6 +554,70 @@ __global__ void vec_epilogue_kernel(const float* __restrict__ acc, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Epilogue of a split-K convolution on a small map: the FP32 accumulator (sum over the K splits, red.global.add) gets
+// the same fused tail as the in-kernel epilogue of spyr_conv2d_fprop: biases, mask-channel stencil, gate, residual,
+// raw + activated BF16 outputs.
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H, int W, int cg,
+                                     const float* __restrict__ bias, const float* __restrict__ bias2,
+                                     const float* __restrict__ bias3, const float* __restrict__ stencil_mask,
+                                     const float* __restrict__ stencil_w, const bf16* __restrict__ dmask, float dmask_slope,
+                                     const bf16* __restrict__ residual, bf16* __restrict__ y_raw, bf16* __restrict__ y_act,
+                                     int act, float act_slope) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * cg) return;
+  const int c = (int)(idx % cg);
+  const long long pix = idx / cg;
+  const int C = cg * 8;
+  float v[8];
+  const float4 a0 = *reinterpret_cast<const float4*>(acc + idx * 8);
+  const float4 a1 = *reinterpret_cast<const float4*>(acc + idx * 8 + 4);
+  v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = c * 8 + j;
+    if (bias != nullptr) v[j] += __ldg(&bias[col]);
+    if (bias2 != nullptr) v[j] += __ldg(&bias2[col]);
+    if (bias3 != nullptr) v[j] += __ldg(&bias3[col]);
+  }
+  if (stencil_mask != nullptr) {
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const long long bbase = pix - (long long)h * W - w;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const float m = __ldg(&stencil_mask[bbase + (long long)hh * W + ww]);
+      if (m != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += m * __ldg(&stencil_w[t * C + c * 8 + j]);
+      }
+    }
+  }
+  if (dmask != nullptr) {
+    float d[8];
+    ld8(dmask + idx * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(d[j] > 0.f)) v[j] *= dmask_slope;
+  }
+  if (residual != nullptr) {
+    float r[8];
+    ld8(residual + idx * 8, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += r[j];
+  }
+  if (y_raw != nullptr) st8(y_raw + idx * 8, v);
+  if (y_act != nullptr) {
+    const float sl = (act == 1) ? 0.f : ((act == 2) ? act_slope : 1.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+    st8(y_act + idx * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generator tail: img = tanh(conv1x1(a; W/sigma) + b), C -> 3 channels, NCHW f32 out  (models.py:58-61,99)
 // ---------------------------------------------------------------------------------------------
 template <int CO>
@@ -856,6 +920,18 @@ extern "C" int spyr_vec_epilogue(const float* acc, const float* bias, const floa
   SPYR_REQUIRE(acc && (mode != 2 || gate) && (out_bf16 == nullptr || ld_bf16 >= N), "vec_epilogue: bad arguments");
   vec_epilogue_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
       acc, bias, add, gate, mode, out_f32, (bf16*)out_bf16, ld_bf16, B, N);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_conv2d_epilogue(const spyr_conv_desc* d, const float* acc, void* stream) {
+  SPYR_REQUIRE(d != nullptr && acc != nullptr, "conv2d_epilogue: bad arguments");
+  SPYR_C8(d->Cout);
+  const long long n = (long long)d->B * d->H * d->W * (d->Cout / 8);
+  conv_epilogue_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, d->B, d->H, d->W, d->Cout / 8, d->bias, d->bias2, d->bias3, d->stencil_mask, d->stencil_w,
+      (const bf16*)d->dmask, d->dmask_slope, (const bf16*)d->residual, (bf16*)d->y_raw, (bf16*)d->y_act, d->act,
+      d->act_slope);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -50,6 +50,18 @@ class Src(object):
         self.x, self.w, self.cin, self.ksize, self.mn, self.per_image = x, w, cin, ksize, mn, per_image
 
 
+def _run_fprop(d, srcs, B, H, W, Cout, out_bytes):
+    if PROFILE is None:
+        call("spyr_conv2d_fprop", C.byref(d))
+        return
+    kred = sum(s.cin * s.ksize * s.ksize for s in srcs)
+    npx = B * H * W
+    nbytes = 2 * npx * sum(s.cin for s in srcs) + 2 * Cout * kred + out_bytes
+    label = "B%d %dx%d Cout=%d %s" % (B, H, W, Cout, "+".join(
+        "%dk%d%s%s" % (s.cin, s.ksize, "T" if s.mn else "", "b" if s.per_image else "") for s in srcs))
+    _profiled("conv_fprop_kernel", 2.0 * npx * Cout * kred, float(nbytes), "spyr_conv2d_fprop", C.byref(d), label)
+
+
 def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=None, stencil_w=None, dmask=None, dmask_slope=1.0, residual=None,
          want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None):
     """out = sum_src conv(src) (+bias, mask stencil, gate, residual).  Returns (y_raw, y_act) (None when not asked).
@@ -70,6 +82,27 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
     d.dmask, d.dmask_slope = ptr(dmask), dmask_slope
     d.residual = ptr(residual)
     y_raw = y_act = None
+    npix = B * H * W
+    if f32_out is None and H * W < 128 and Cout % 8 == 0 and not any(s.per_image for s in srcs):
+        # 4x4 / 8x8 maps: a handful of output tiles cannot fill 148 SMs -> split the reduction over CTAs into an FP32
+        # accumulator and apply the fused epilogue in a second, tiny kernel
+        ksteps = sum(((s.cin + 63) // 64) * s.ksize * s.ksize for s in srcs)
+        tiles = ((npix + 127) // 128) * ((Cout + 255) // 256)
+        nsplit = max(1, min(ksteps // 4, 148 // tiles))
+        if nsplit > 1:
+            acc = torch.zeros((npix, Cout), dtype=F32, device=dev)
+            d.y_f32, d.splits = acc.data_ptr(), nsplit
+            _run_fprop(d, srcs, B, H, W, Cout, 4 * npix * Cout)
+            d.y_f32, d.splits = None, 0
+            if want_raw:
+                y_raw = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+                d.y_raw = y_raw.data_ptr()
+            if want_act:
+                y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+                d.y_act = y_act.data_ptr()
+            d.act, d.act_slope = act, act_slope
+            call("spyr_conv2d_epilogue", C.byref(d), acc.data_ptr())
+            return y_raw, y_act
     if f32_out is not None:
         d.y_f32, d.f32_store, d.splits = f32_out.data_ptr(), int(f32_store), splits
     else:
@@ -80,16 +113,8 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
             y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
             d.y_act = y_act.data_ptr()
         d.act, d.act_slope = act, act_slope
-    if PROFILE is None:
-        call("spyr_conv2d_fprop", C.byref(d))
-    else:
-        kred = sum(s.cin * s.ksize * s.ksize for s in srcs)
-        npx = B * H * W
-        nbytes = 2 * npx * sum(s.cin for s in srcs) + 2 * Cout * kred + (4 if f32_out is not None else 2) * npx * Cout * (
-            int(want_raw) + int(want_act) if f32_out is None else 1)
-        label = "B%d %dx%d Cout=%d %s" % (B, H, W, Cout, "+".join(
-            "%dk%d%s%s" % (s.cin, s.ksize, "T" if s.mn else "", "b" if s.per_image else "") for s in srcs))
-        _profiled("conv_fprop_kernel", 2.0 * npx * Cout * kred, float(nbytes), "spyr_conv2d_fprop", C.byref(d), label)
+    out_bytes = (4 if f32_out is not None else 2) * npix * Cout * (int(want_raw) + int(want_act) if f32_out is None else 1)
+    _run_fprop(d, srcs, B, H, W, Cout, out_bytes)
     return y_raw, y_act
 
 
