@@ -10,7 +10,7 @@ LIB       := $(PKG)/libspyramid_b200.so
 
 all: $(LIB)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/spyramid_b200.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/conv_halo_common.cuh include/spyramid_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -1,26 +1,19 @@
-// Persistent, halo-tiled implicit-GEMM convolution for feature maps of 16x16 pixels and larger (sm_100a).
+// CTA-pair (tcgen05 cta_group::2) variant of the halo-tiled convolution for layers with >= 128 output channels.
 //
-// Why a second conv kernel: with one TMA load per (tap, 64-channel chunk) the kernel in conv_tc.cu moves
-// 9 x 16 KB of activations from L2 to shared memory for every 128-pixel tile and is L2->SMEM bandwidth bound
-// (~12 TB/s chip-wide, measured: 24 % of the tensor peak).  Here the activation operand of a 3x3 convolution is ONE
-// halo tile per 64-channel chunk -- (8+2) x (16*MSUB+2) pixels, 128 B per pixel, SWIZZLE_128B, written by a single
-// TMA box whose out-of-bounds rows are the convolution's zero padding -- and the nine taps are nine tcgen05.mma
-// A-descriptors that start at different 128-byte rows of that tile: output pixel (th, tw) of tap (dy, dx) reads halo
-// row (th+dy)*(8+2) + (tw+dx), so every 8-pixel output row is an 8-row core-matrix group and the groups are a
-// constant (8+2)*128 bytes apart (the descriptor's stride-byte-offset).  The swizzle XOR is a function of the
-// absolute shared-memory address, so unaligned start rows need no base offset (validated by tests/native, `halo`).
+// Why: ncu (l1tex__data_pipe_tc_wavefronts_mem_shared) shows tcgen05.mma fetching its shared-memory operands at about
+// 64 B/clk per SM.  A single-CTA M=128 instruction reads 4 KB of activations plus the whole N x 16 weight slice, so it
+// is operand-bound below N = 256 (N=128: 8 KB per 64 ideal clocks).  With cta_group::2 two SMs execute one M=256
+// instruction: each SM reads its own 128 activation rows but only HALF of the weight slice, i.e. per SM 4 KB + N*16 B:
+// N=256 -> 8 KB per 128 clocks (exactly the fetch rate), N=128 -> 6 KB per 64 clocks.
 //
-//   tile          256 (MSUB=2) or 128 output pixels of one image x BLOCK_N output channels
-//   A traffic     1 halo tile per chunk instead of 9 tap tiles  (6.4x less)
-//   B traffic     each weight stage (tap, chunk) feeds MSUB x 4 MMAs (2x less per FLOP at MSUB=2)
-//   schedule      persistent CTAs (grid = #SMs), static round-robin over tiles
-//   pipelines     A ring (2 halo buffers), B ring (weight stages), 2 TMEM accumulator sets: the epilogue of tile i
-//                 overlaps the TMA + MMA of tile i+1
-//   warps         0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (two column halves x four
-//                 TMEM lane quarters)
-//
-// Same sources / epilogue contract as spyr_conv2d_fprop (see include/spyramid_b200.h); split-K and maps smaller than
-// 16x8 stay on the conv_tc.cu kernel.
+// Structure = conv_halo.cu with the pair protocol:
+//   * cluster of 2 CTAs; CTA r owns pixel tile 2*pair + r (its own halo buffers, its own TMEM rows) and weight rows
+//     [r*N/2, (r+1)*N/2) of every (tap, chunk) slice;
+//   * both CTAs issue TMA with .cta_group::2 so the bytes are counted on the LEADER's (rank 0) full barriers;
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256) and commits with .multicast::cluster to the empty /
+//     accumulator-full barriers of BOTH CTAs;
+//   * the epilogue warps of both CTAs drain their own TMEM half and arrive on the leader's accumulator-empty barrier
+//     (CTA 1 through mapa + mbarrier.arrive.shared::cluster).
 #include "common.cuh"
 #include "../../include/spyramid_b200.h"
 #include "conv_halo_common.cuh"
@@ -30,8 +23,68 @@ extern void spyr_count_launch();
 namespace {
 using namespace halo;
 
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address -> same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
+conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -44,10 +97,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   uint64_t* acc_full = b_empty + p.b_stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* epi_const = reinterpret_cast<float*>(tmem_holder + 4);  // [2][11][block_n]: bias sum + 10 stencil rows
+  float* epi_const = reinterpret_cast<float*>(tmem_holder + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int half_n = p.block_n >> 1;  // weight rows (output channels) this CTA stages per (tap, chunk)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) {
@@ -66,39 +123,41 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS);
+      mbar_init(&acc_empty[i], 2 * EPI_WARPS);
     }
     fence_barrier_init();
   }
+  cluster_sync_all();  // both CTAs' barriers exist before anything can signal them remotely
   if (warp == 2) {
-    tmem_alloc(tmem_holder, p.tmem_cols);
-    tmem_relinquish();
+    tmem_alloc2(tmem_holder, p.tmem_cols);
+    tmem_relinquish2();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const int b_chunks = (p.block_n + 63) >> 6;
   const int th_rows = 16 * p.msub;
+  const int total_pairs = (p.m_tiles >> 1) * p.n_tiles;
 
   if (warp == 0) {
-    if (elect_one()) {
-      // ===== TMA producer =====
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own halo tiles, own half of every weight slice =====
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      for (int t = pair; t < total_pairs; t += num_pairs) {
+        const int pm = t % (p.m_tiles >> 1), n_tile = t / (p.m_tiles >> 1);
+        const int m_tile = 2 * pm + (int)rank;
         const int w0 = (m_tile % p.tiles_w) * 8;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
         const int n0 = m_tile / (p.tiles_w * p.tiles_h);
-        const int n_off = n_tile * p.block_n;
+        const int n_off = n_tile * p.block_n + (int)rank * half_n;
         for (int s = 0; s < p.nsrc; ++s) {
           const int bd = p.border[s];
           const int taps = bd ? 9 : 1;
           for (int c = 0; c < p.kchunks[s]; ++c) {
             mbar_wait(&a_empty[abuf], aph ^ 1);
-            mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(p.a_rows[s] * 128));
-            tma_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
+            if (leader) mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(2 * p.a_rows[s] * 128));
+            tma2_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
             if (++abuf == A_BUFS) {
               abuf = 0;
               aph ^= 1;
@@ -106,14 +165,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[bst], bph ^ 1);
               uint8_t* b_dst = b_ring + bst * p.b_stage_bytes;
+              if (leader) mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
               if (p.wmn[s]) {
-                mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(b_chunks * 8192));
                 const int wtap = p.wpi[s] ? n0 : (bd ? 8 - tap : 0);
-                for (int j = 0; j < b_chunks; ++j)
-                  tma_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
+                for (int j = 0; j < (half_n >> 6); ++j)
+                  tma2_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
               } else {
-                mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
-                tma_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
+                tma2_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
               }
               if (++bst == p.b_stages) {
                 bst = 0;
@@ -125,93 +183,89 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: ONE thread runs the whole loop.  Descriptors are 64-bit integers advanced by plain adds on the
-    // 14-bit start-address field (16-byte units); recomputing them per MMA made this thread, not the tensor pipe, the
-    // bottleneck (ncu: 22 dependent instructions per tcgen05.mma).
-    if (lane == 0) {
-      const uint32_t idesc_k = umma_idesc_bf16(128, p.block_n, 0, 0);
-      const uint32_t idesc_mn = umma_idesc_bf16(128, p.block_n, 0, 1);
-      const uint64_t desc_base = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // version 1, SWIZZLE_128B
+    if (lane == 0 && leader) {
+      // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
+      const uint32_t idesc_k = umma_idesc_bf16(256, p.block_n, 0, 0);
+      const uint32_t idesc_mn = umma_idesc_bf16(256, p.block_n, 0, 1);
+      const uint64_t desc_base = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       const uint32_t a_ring_lo = (smem_u32(a_ring) & 0x3FFFF) >> 4;
       const uint32_t b_ring_lo = (smem_u32(b_ring) & 0x3FFFF) >> 4;
       const uint32_t a_buf16 = (uint32_t)p.a_buf_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int t = pair; t < total_pairs; t += num_pairs, ++it) {
         const int buf = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[buf], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.msub * p.bn_cols);
-        uint32_t accum = 0;  // 0 only for the first MMA of each sub-tile accumulator
+        uint32_t accum = 0;
         for (int s = 0; s < p.nsrc; ++s) {
           const int bd = p.border[s];
           const int taps = bd ? 9 : 1;
-          const uint32_t row16 = 8;                                  // one 128-byte pixel row in 16-byte units
-          const uint32_t pitch16 = (uint32_t)(8 + 2 * bd) * row16;  // consecutive 8-pixel output rows
-          const uint32_t sub16 = 16u * pitch16;                      // second 8x16 sub-tile
+          const uint32_t pitch16 = (uint32_t)(8 + 2 * bd) * 8u;
+          const uint32_t sub16 = 16u * pitch16;
           const bool mn = p.wmn[s] != 0;
           const uint64_t a_hi = desc_base | ((uint64_t)pitch16 << 32);
           const uint64_t b_hi = mn ? (desc_base | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32))
                                    : (desc_base | ((uint64_t)(1024 >> 4) << 32));
-          const uint32_t bk16 = mn ? (2048u >> 4) : 2u;  // K advance of 16 elements
+          const uint32_t bk16 = mn ? (2048u >> 4) : 2u;
           const uint32_t idesc = mn ? idesc_mn : idesc_k;
           for (int c = 0; c < p.kchunks[s]; ++c) {
             mbar_wait(&a_full[abuf], aph);
             const uint32_t a_lo = a_ring_lo + (uint32_t)abuf * a_buf16;
-            uint32_t row0 = 0;  // halo row of output pixel (0,0) for the current tap: dy*10 + dx
+            uint32_t row0 = 0;
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_full[bst], bph);
               tc_fence_after();
               const uint64_t db0 = b_hi | (uint64_t)(b_ring_lo + (uint32_t)bst * b_stage16);
-              const uint64_t da0 = a_hi | (uint64_t)(a_lo + row0 * row16);
+              const uint64_t da0 = a_hi | (uint64_t)(a_lo + row0 * 8u);
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                umma_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
+                umma2_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
               if (p.msub == 2) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  umma_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k), idesc,
-                            k == 0 ? accum : 1u);
+                  umma2_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k), idesc,
+                             k == 0 ? accum : 1u);
               }
               accum = 1;
-              umma_commit(&b_empty[bst]);
+              umma2_commit_mc(&b_empty[bst]);
               if (++bst == p.b_stages) {
                 bst = 0;
                 bph ^= 1;
               }
-              row0 += ((tap % 3) == 2) ? 8u : 1u;  // dx wraps: next halo row block (10 - 2)
+              row0 += ((tap % 3) == 2) ? 8u : 1u;
             }
-            umma_commit(&a_empty[abuf]);
+            umma2_commit_mc(&a_empty[abuf]);
             if (++abuf == A_BUFS) {
               abuf = 0;
               aph ^= 1;
             }
           }
         }
-        umma_commit(&acc_full[buf]);
+        umma2_commit_mc(&acc_full[buf]);
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue (both CTAs, own TMEM rows = own pixel tile, all block_n columns) =====
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int m = q * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
+    const int et = threadIdx.x - 128;
     int it = 0;
     int staged_n_off = -1, cbuf = 1;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int t = pair; t < total_pairs; t += num_pairs, ++it) {
       const int buf = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      const int pm = t % (p.m_tiles >> 1), n_tile = t / (p.m_tiles >> 1);
+      const int m_tile = 2 * pm + (int)rank;
       const int w0 = (m_tile % p.tiles_w) * 8;
       const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
       const int n = m_tile / (p.tiles_w * p.tiles_h);
       const int n_off = n_tile * p.block_n;
       if (n_off != staged_n_off) {
-        // new N block: stage its constants into the other buffer, then one barrier among the 8 epilogue warps.  Warps
-        // reach this barrier only after finishing the previous tile, so the buffer being overwritten is no longer read.
         cbuf ^= 1;
         float* dst = epi_const + cbuf * 11 * p.block_n;
         for (int c = et; c < p.block_n; c += EPI_WARPS * 32) {
@@ -225,7 +279,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           dst[c] = b;
           if (p.stencil_w != nullptr) {
 #pragma unroll
-            for (int t = 0; t < 10; ++t) dst[(1 + t) * p.block_n + c] = col < p.Cout ? __ldg(&p.stencil_w[t * p.Cout + col]) : 0.f;
+            for (int tt = 0; tt < 10; ++tt)
+              dst[(1 + tt) * p.block_n + c] = col < p.Cout ? __ldg(&p.stencil_w[tt * p.Cout + col]) : 0.f;
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -242,11 +297,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           const int h = h0 + sub * 16 + (m >> 3);
           bool all0 = true, all1 = true;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+          for (int tt = 0; tt < 9; ++tt) {
+            const int hh = h + tt / 3 - 1, ww = w + tt % 3 - 1;
             float v = 0.f;
             if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) v = __ldg(&p.stencil_mask[((size_t)n * p.H + hh) * p.W + ww]);
-            mk[sub][t] = v;
+            mk[sub][tt] = v;
             all0 = all0 && (v == 0.f);
             all1 = all1 && (v == 1.f);
           }
@@ -268,19 +323,20 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still be reading its TMEM half / our barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    tmem_dealloc2(tmem_base, p.tmem_cols);
   }
 }
 
-uint32_t pow2_at_least(int n, uint32_t lo) {
+uint32_t pow2_at_least2(int n, uint32_t lo) {
   uint32_t c = lo;
   while ((int)c < n) c <<= 1;
   return c;
@@ -288,45 +344,39 @@ uint32_t pow2_at_least(int n, uint32_t lo) {
 
 }  // namespace
 
-// Returns 0 on launch, -1 when the problem is not eligible (caller falls back to the per-tap kernel), >0 on error.
-int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
+// Returns 0 on launch, -1 when not eligible (the caller falls back to conv_halo.cu), >0 on error.
+int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   if (d->H < 16 || d->W < 8 || (d->H % 16) != 0 || (d->W % 8) != 0) return -1;
-  if (d->splits > 1) return -1;
+  if (d->splits > 1 || d->block_n != 0) return -1;
   if (d->y_f32 != nullptr && !d->f32_store) return -1;
-  if (d->y_f32 == nullptr && (d->Cout % 8) != 0) return -1;
+  if (d->Cout < 128 || (d->Cout % 128) != 0) return -1;
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.nsrc = d->nsrc;
-  int bn = d->block_n;
-  if (bn == 0) {
-    // tcgen05.mma reads both operands from shared memory at ~64 B/clk/SM (measured with ncu: tc wavefronts), so the
-    // 4 KB A slice of every M=128 instruction costs 64 clk: only N >= 256 per instruction keeps the tensor pipe above
-    // 2/3 busy.  Wide layers therefore use one 128-pixel sub-tile x 256 channels, narrow ones two sub-tiles x Cout.
-    bn = d->Cout >= 256 ? 256 : (d->Cout >= 128 ? 128 : ((d->Cout + 15) / 16) * 16);
-    if (bn < 32) bn = 32;
-  }
-  if (bn > 256 || bn % 16 != 0) return -1;
+  const int bn = d->Cout >= 256 ? 256 : 128;
   p.msub = (d->H % 32 == 0 && bn <= 128) ? 2 : 1;
   p.block_n = bn;
-  p.bn_cols = (int)pow2_at_least(bn, 32);
-  p.tmem_cols = pow2_at_least(2 * p.msub * p.bn_cols, 32);
+  p.bn_cols = bn;
+  p.tmem_cols = pow2_at_least2(2 * p.msub * p.bn_cols, 32);
   if (p.tmem_cols > 512) return -1;
   p.tiles_w = d->W / 8;
   p.tiles_h = d->H / (16 * p.msub);
   p.m_tiles = p.tiles_w * p.tiles_h * d->B;
-  p.n_tiles = ceil_div(d->Cout, bn);
+  if (p.m_tiles & 1) return -1;
+  p.n_tiles = d->Cout / bn;
   p.total_tiles = p.m_tiles * p.n_tiles;
   HaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
   int max_rows = 0;
-  p.b_stage_bytes = bn * 128;
+  const int half_n = bn / 2;
+  p.b_stage_bytes = half_n * 128;
   for (int s = 0; s < d->nsrc; ++s) {
     const spyr_conv_src& src = d->src[s];
     SPYR_REQUIRE(src.ksize == 1 || src.ksize == 3, "conv2d_fprop: ksize must be 1 or 3");
     SPYR_REQUIRE(src.cin % 8 == 0 && src.cin > 0, "conv2d_fprop: cin=%d must be a multiple of 8", src.cin);
     SPYR_REQUIRE(((uintptr_t)src.x & 15) == 0 && ((uintptr_t)src.w & 15) == 0, "conv2d_fprop: unaligned pointer");
     SPYR_REQUIRE(!src.w_per_image || src.ksize == 1, "conv2d_fprop: per-image weights need ksize 1");
-    SPYR_REQUIRE(!src.w_mn_major || (d->Cout % 8 == 0), "conv2d_fprop: MN-major weights need Cout %% 8 == 0");
     const int bd = src.ksize == 3 ? 1 : 0;
     p.border[s] = bd;
     p.kchunks[s] = ceil_div(src.cin, KC);
@@ -335,7 +385,7 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     const int bw = 8 + 2 * bd, bh = 16 * p.msub + 2 * bd;
     p.a_rows[s] = bw * bh;
     if (p.a_rows[s] > max_rows) max_rows = p.a_rows[s];
-    if (src.w_mn_major && ceil_div(bn, 64) * 8192 > p.b_stage_bytes) p.b_stage_bytes = ceil_div(bn, 64) * 8192;
+    if (src.w_mn_major && (half_n / 64) * 8192 > p.b_stage_bytes) p.b_stage_bytes = (half_n / 64) * 8192;
     {
       uint64_t dims[4] = {(uint64_t)src.cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
       uint64_t strides[3] = {(uint64_t)src.cin * 2, (uint64_t)d->W * src.cin * 2, (uint64_t)d->H * d->W * src.cin * 2};
@@ -351,7 +401,7 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     } else {
       uint64_t dims[3] = {(uint64_t)src.cin, (uint64_t)d->Cout, wslices};
       uint64_t strides[2] = {(uint64_t)src.cin * 2, (uint64_t)d->Cout * src.cin * 2};
-      uint32_t box[3] = {KC, (uint32_t)bn, 1};
+      uint32_t box[3] = {KC, (uint32_t)half_n, 1};
       if (spyr_tmap_encode(&maps.w[s], src.w, 3, dims, strides, box, 1)) return 3;
     }
   }
@@ -360,10 +410,9 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     maps.w[s] = maps.w[0];
   }
   p.a_buf_bytes = ceil_div(max_rows * 128, 1024) * 1024;
-  const int budget = 200 * 1024 - A_BUFS * p.a_buf_bytes;
+  const int budget = 196 * 1024 - A_BUFS * p.a_buf_bytes;
   int stages = budget / p.b_stage_bytes;
   if (stages > 12) stages = 12;
-  if (d->stages > 0 && d->stages < stages) stages = d->stages;
   if (stages < 2) return -1;
   p.b_stages = stages;
   p.bias = d->bias; p.bias2 = d->bias2; p.bias3 = d->bias3;
@@ -377,7 +426,7 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
                             (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   static int num_sms = 0;
@@ -386,9 +435,23 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     SPYR_CHECK_CUDA(cudaGetDevice(&dev));
     SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_halo_kernel<<<grid, THREADS, smem_bytes, stream>>>(maps, p);
+  const int total_pairs = (p.m_tiles / 2) * p.n_tiles;
+  int pairs = num_sms / 2;
+  if (pairs > total_pairs) pairs = total_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel, maps, p));
   spyr_count_launch();
-  SPYR_LAUNCH_CHECK();
   return 0;
 }

@@ -20,6 +20,7 @@
 
 extern void spyr_count_launch();
 int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream);
+int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream);
 int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream);
 
 namespace {
@@ -555,7 +556,13 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
     // maps of 16x8 pixels and larger run on the persistent halo-tiled kernel (conv_halo.cu); SPYR_CONV_LEGACY=1 forces
     // the per-tap kernel below (A/B measurements)
     static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
+    static const bool no_pair = getenv("SPYR_CONV_NO_PAIR") != nullptr;
     if (!legacy) {
+      if (!no_pair) {
+        // >= 128 output channels: CTA pairs (tcgen05 cta_group::2) halve the weight operand fetched per SM
+        const int rc2 = spyr_conv_halo2_launch(d, stream);
+        if (rc2 >= 0) return rc2;
+      }
       const int rc = spyr_conv_halo_launch(d, stream);
       if (rc >= 0) return rc;
     }
