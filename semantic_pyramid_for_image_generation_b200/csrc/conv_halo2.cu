@@ -1,10 +1,11 @@
 // CTA-pair (tcgen05 cta_group::2) variant of the halo-tiled convolution for layers with >= 128 output channels.
 //
-// Why: ncu (l1tex__data_pipe_tc_wavefronts_mem_shared) shows tcgen05.mma fetching its shared-memory operands at about
-// 64 B/clk per SM.  A single-CTA M=128 instruction reads 4 KB of activations plus the whole N x 16 weight slice, so it
-// is operand-bound below N = 256 (N=128: 8 KB per 64 ideal clocks).  With cta_group::2 two SMs execute one M=256
-// instruction: each SM reads its own 128 activation rows but only HALF of the weight slice, i.e. per SM 4 KB + N*16 B:
-// N=256 -> 8 KB per 128 clocks (exactly the fetch rate), N=128 -> 6 KB per 64 clocks.
+// Why: a single-CTA M=128 instruction reads 4 KB of activations plus the whole N x 16 weight slice from shared memory,
+// and every CTA streams the full weight slice of each (tap, chunk) from L2.  With cta_group::2 two SMs execute one
+// M=256 instruction: each SM stages and reads its own 128 activation rows but only HALF of the weight slice.
+// Measured (profiles/r01_*pair*): TMA traffic of a 256->256 @64x64 launch drops from 796 MB to 437 MB and the shared-
+// memory operand wavefronts per SM from 96 to 64 per instruction, while the time per instruction stays ~235 clk
+// (ideal 128) -- i.e. on this shape the pair kernel buys L2 / shared-memory head-room, not yet tensor-pipe time.
 //
 // Structure = conv_halo.cu with the pair protocol:
 //   * cluster of 2 CTAs; CTA r owns pixel tile 2*pair + r (its own halo buffers, its own TMEM rows) and weight rows
@@ -354,7 +355,7 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.nsrc = d->nsrc;
-  const int bn = d->Cout >= 256 ? 256 : 128;
+  const int bn = (d->Cout % 256 == 0) ? 256 : 128;  // whole N blocks only (e.g. 384 = 3 x 128)
   p.msub = (d->H % 32 == 0 && bn <= 128) ? 2 : 1;
   p.block_n = bn;
   p.bn_cols = bn;
