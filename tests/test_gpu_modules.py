@@ -267,3 +267,50 @@ def test_training_step_matches_reference_golden():
     for k in ("layers.0.main_block.0.weight_u", "embedding.weight_v"):
         assert rel_l2(sd[k], gold["post_step_d"][k]) < 1e-3, k
     assert all(p.grad is None for p in D.parameters())  # D weight gradients are not produced in the generator phase
+
+
+def test_model_wrapper_train_entry_point_and_checkpoint(tmp_path):
+    """Drop-in driver: ModelWrapper(...).train(epochs=1) over a tiny synthetic loader in the collate format of data.py:76-90,
+    then the checkpoint it wrote is loaded back (keys of model_wrapper.py:215-223) and inference() produces the 7x7 grid."""
+    import os
+    from semantic_pyramid_for_image_generation_b200 import misc, models
+    from semantic_pyramid_for_image_generation_b200.model_wrapper import ModelWrapper
+    from semantic_pyramid_for_image_generation_b200.optim import FusedAdam
+
+    class Data(torch.utils.data.Dataset):
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(i)
+            img = torch.rand(3, 256, 256, generator=g) * 2 - 1
+            label = torch.nn.functional.one_hot(torch.tensor(i % 365), 365).long()
+            return img, label, misc.get_masks_for_inference(i % 7)
+
+    def collate(batch):
+        images = torch.stack([b[0] for b in batch])
+        labels = torch.stack([b[1] for b in batch])
+        masks = [torch.stack([b[2][lvl] for b in batch]) for lvl in range(7)]
+        return images, labels, masks
+
+    loader = torch.utils.data.DataLoader(Data(), batch_size=2, collate_fn=collate, drop_last=True)
+    torch.manual_seed(0)
+    G, D, V = models.Generator(channels_factor=2), models.Discriminator(channel_factor=2), models.VGG16()
+    G.cuda(), D.cuda(), V.cuda()
+    wrapper = ModelWrapper(G, D, loader, loader, vgg16=V, generator_optimizer=FusedAdam(G.parameters(), lr=1e-5),
+                           discriminator_optimizer=FusedAdam(D.parameters(), lr=1e-5), save_data_path=str(tmp_path))
+    u_before = G.linear_layer.weight_u.clone()
+    wrapper.train(epochs=1, device="cuda")
+    assert len(wrapper.logger.metrics["loss_generator"]) == 4
+    assert all(map(lambda v: v == v and abs(v) < 1e3, wrapper.logger.metrics["loss_discriminator_real"]))  # finite
+    assert not torch.equal(u_before, G.linear_layer.weight_u)
+    ckpts = [f for f in os.listdir(wrapper.path_save_models) if f.endswith(".pt")]
+    assert ckpts == ["checkpoint_000.pt"]
+    ck = torch.load(os.path.join(wrapper.path_save_models, ckpts[0]), weights_only=False)
+    assert set(ck.keys()) == {"generator", "discriminator", "generator_optimizer", "discriminator_optimizer"}
+    models.Generator(channels_factor=2).load_state_dict(ck["generator"])
+    assert float(ck["generator_optimizer"]["state"][0]["step"]) == 4.0
+    grid = wrapper.inference(device="cuda")
+    assert tuple(grid.shape) == (49, 3, 256, 256) and bool(torch.isfinite(grid).all())
+    assert float(grid.abs().max()) <= 1.0
+    assert os.path.isfile(os.path.join(wrapper.path_save_metrics, "loss_generator.pt"))

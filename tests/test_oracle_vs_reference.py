@@ -202,3 +202,39 @@ def test_masks_bit_exact(ref):
             assert a.shape == b.shape and torch.equal(a, b)
         n_spatial += int(any(0 < float(m.mean()) < 1 for m in mine))
     assert n_spatial > 0
+
+
+def test_checkpoint_interchange_with_reference_modules(ref, tmp_path):
+    """a reference checkpoint (model_wrapper.py:215-223) loads into the B200 modules and back, including the
+    optimizer state, with strict key/shape matching."""
+    from semantic_pyramid_for_image_generation_b200 import models as new_models
+    from semantic_pyramid_for_image_generation_b200.optim import FusedAdam
+    ref_models, _, _ = ref
+    for cf in (1, 2):
+        g_ref, d_ref = ref_models.Generator(channels_factor=cf), ref_models.Discriminator(channel_factor=cf)
+        g_new, d_new = new_models.Generator(channels_factor=cf), new_models.Discriminator(channel_factor=cf)
+        g_opt_ref = torch.optim.Adam(g_ref.parameters(), lr=1e-5)
+        for p in g_ref.parameters():
+            p.grad = torch.ones_like(p)
+        g_opt_ref.step()
+        path = tmp_path / ("checkpoint_%d.pt" % cf)
+        torch.save({"generator": g_ref.state_dict(), "discriminator": d_ref.state_dict(),
+                    "generator_optimizer": g_opt_ref.state_dict()}, path)
+        ckpt = torch.load(path, weights_only=False)
+        g_new.load_state_dict(ckpt["generator"])  # strict
+        d_new.load_state_dict(ckpt["discriminator"])
+        g_opt_new = FusedAdam(g_new.parameters(), lr=1e-5)
+        g_opt_new.load_state_dict(ckpt["generator_optimizer"])
+        assert len(g_opt_new.state_dict()["state"]) == len(ckpt["generator_optimizer"]["state"])
+        for k, v in g_ref.state_dict().items():
+            assert torch.equal(v, g_new.state_dict()[k]), k
+        # and back: a checkpoint written by the B200 modules loads into the reference
+        g_ref2, d_ref2 = ref_models.Generator(channels_factor=cf), ref_models.Discriminator(channel_factor=cf)
+        g_ref2.load_state_dict(g_new.state_dict())
+        d_ref2.load_state_dict(d_new.state_dict())
+        torch.optim.Adam(g_ref2.parameters(), lr=1e-5).load_state_dict(g_opt_new.state_dict())
+        assert [n for n, _ in g_ref2.named_parameters()] == [n for n, _ in g_new.named_parameters()]
+        assert [n for n, _ in d_ref2.named_parameters()] == [n for n, _ in d_new.named_parameters()]
+    v_ref, v_new = ref_models.VGG16(), new_models.VGG16()
+    v_new.load_state_dict(v_ref.state_dict())
+    v_ref.load_state_dict(v_new.state_dict())
