@@ -222,7 +222,13 @@ int spyr_dhead_out_fwd(const float* cls, const float* feat, const float* emb_w, 
 int spyr_dhead_out_bwd(const float* g, const float* feat, const float* emb_w, const float* sigma, const int* idx,
                        float* g_cls, float* g_feat, float* g_embw, int B, int E, void* stream);
 
-/* attention-map softmax over keys (models.py:266) and its backward */
+/* Fused SAGAN attention forward (models.py:262-270): o[b,q,:] = softmax_k(q[b,q,:] . k[b,k,:]) @ v[b,k,:], no 1/sqrt(d).
+ * q [B,HW,d], k [B,nk,d], v [B,nk,dv], o [B,HW,dv] BF16 row-major (the NHWC maps of the 1x1 convolutions);
+ * p_out (may be NULL) receives the normalised attention map [B,HW,nk] in BF16 for the backward pass.
+ * Limits: HW % 128 == 0, 8 <= d <= 64, nk in {64,128,192,256}, dv in {64,128}. */
+int spyr_sagan_attention_fwd(const void* q, const void* k, const void* v, void* o, void* p_out, int B, int HW, int d, int nk,
+                             int dv, void* stream);
+/* attention-map softmax over keys (models.py:266) and its backward (unfused path / backward pass) */
 int spyr_softmax_rows_fwd(const float* s, void* p, long long rows, int n, void* stream);
 int spyr_softmax_rows_bwd(const void* p, const float* dp, void* ds, long long rows, int n, void* stream);
 

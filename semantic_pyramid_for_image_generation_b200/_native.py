@@ -99,6 +99,7 @@ _SIGNATURES = {
     "spyr_linear_bwd_w": [P, P, c_float, P, P, c_float, P, P, c_int, c_int, c_int, P],
     "spyr_dhead_out_fwd": [P, P, P, P, P, P, c_int, c_int, P],
     "spyr_dhead_out_bwd": [P, P, P, P, P, P, P, P, c_int, c_int, P],
+    "spyr_sagan_attention_fwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "spyr_softmax_rows_fwd": [P, P, c_ll, c_int, P],
     "spyr_softmax_rows_bwd": [P, P, P, c_ll, c_int, P],
     "spyr_lsgan_fwd": [P, c_ll, c_float, P, P],

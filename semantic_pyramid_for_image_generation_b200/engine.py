@@ -54,6 +54,14 @@ def _f32c(t):
 # ------------------------------------------------------------------------------------------------
 # SelfAttention (models.py:249-275); x is the raw NHWC residual stream
 # ------------------------------------------------------------------------------------------------
+FUSED_ATTENTION = True  # tests flip this to compare the fused kernel with the per-image GEMM path
+
+
+def fused_attention_ok(hw, d, nk, dv):
+    return FUSED_ATTENTION and hw % 128 == 0 and 8 <= d <= 64 and d % 8 == 0 and nk % 64 == 0 and 64 <= nk <= 256 \
+        and dv in (64, 128)
+
+
 def attention_forward(att, key, st, x, want_act, save):
     B, H, W, Cc = x.shape
     d, dv, nk = Cc // 8, Cc // 2, (H * W) // 4
@@ -62,11 +70,17 @@ def attention_forward(att, key, st, x, want_act, save):
     k, _ = ops.conv(B, H // 2, W // 2, d, [Src(xp, st.w(key + ".key_convolution"), Cc, 1)], bias=att.key_convolution.bias)
     v, _ = ops.conv(B, H // 2, W // 2, dv, [Src(xp, st.w(key + ".value_convolution"), Cc, 1)],
                     bias=att.value_convolution.bias)
-    S = torch.empty((B, H * W, nk), dtype=F32, device=x.device)
-    ops.conv(B, H, W, nk, [Src(q, k, d, 1, per_image=True)], f32_out=S, f32_store=True)
-    Pm = torch.empty((B, H, W, nk), dtype=BF16, device=x.device)
-    call("spyr_softmax_rows_fwd", S.data_ptr(), Pm.data_ptr(), B * H * W, nk)
-    O, _ = ops.conv(B, H, W, dv, [Src(Pm, v, nk, 1, mn=True, per_image=True)])
+    if fused_attention_ok(H * W, d, nk, dv):
+        # one kernel: S = Q K^T, softmax over keys, O = P V; the attention map is written once (BF16) only for backward
+        Pm = torch.empty((B, H, W, nk), dtype=BF16, device=x.device) if save else None
+        O = torch.empty((B, H, W, dv), dtype=BF16, device=x.device)
+        call("spyr_sagan_attention_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), O.data_ptr(), ptr(Pm), B, H * W, d, nk, dv)
+    else:
+        S = torch.empty((B, H * W, nk), dtype=F32, device=x.device)
+        ops.conv(B, H, W, nk, [Src(q, k, d, 1, per_image=True)], f32_out=S, f32_store=True)
+        Pm = torch.empty((B, H, W, nk), dtype=BF16, device=x.device)
+        call("spyr_softmax_rows_fwd", S.data_ptr(), Pm.data_ptr(), B * H * W, nk)
+        O, _ = ops.conv(B, H, W, dv, [Src(Pm, v, nk, 1, mn=True, per_image=True)])
     t, _ = ops.conv(B, H, W, Cc, [Src(O, st.w(key + ".attention_convolution"), dv, 1)],
                     bias=att.attention_convolution.bias)
     out = torch.empty_like(x)

@@ -473,3 +473,24 @@ def test_attention_forward_backward(ops):
         if float(ref.norm()) < 1e-6 * float(sd["a.value_convolution.bias"].grad.norm()):
             continue  # key bias: softmax shift invariance makes this gradient analytically zero
         assert rel_l2(mine, ref) < 2e-2, name
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 32, 32, 128), (2, 16, 32, 16, 64), (2, 16, 16, 8, 64)])
+def test_fused_sagan_attention_forward(ops, shape):
+    """One-kernel attention (S = QK^T, softmax over keys, O = PV) against torch on BF16-representable q, k, v."""
+    from semantic_pyramid_for_image_generation_b200 import ops as o
+    B, H, W, d, dv = shape
+    hw, nk = H * W, (H * W) // 4
+    g = gen(17)
+    qq = q(torch.randn(B, hw, d, generator=g))
+    kk = q(torch.randn(B, nk, d, generator=g) * 0.7)
+    vv = q(torch.randn(B, nk, dv, generator=g))
+    p_ref = torch.softmax(torch.einsum("bqd,bkd->bqk", qq, kk), dim=-1)
+    o_ref = torch.einsum("bqk,bkc->bqc", p_ref, vv)
+    out = torch.empty(B, hw, dv, dtype=torch.bfloat16, device="cuda")
+    pm = torch.empty(B, hw, nk, dtype=torch.bfloat16, device="cuda")
+    o.call("spyr_sagan_attention_fwd", qq.bfloat16().cuda(), kk.bfloat16().cuda(), vv.bfloat16().cuda(), out, pm, B, hw, d,
+           nk, dv)
+    assert rel_l2(pm, p_ref) < TOL_BF16
+    assert rel_l2(out, o_ref) < TOL_BF16
+    assert float((pm.float().sum(-1) - 1).abs().max()) < 2e-2
