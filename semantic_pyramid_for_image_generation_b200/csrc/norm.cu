@@ -164,20 +164,20 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 //                 mode 1: a = up2(lrelu(aff(x))), xu = up2(x)   (generator block, models.py:295-298,308)
 //                 mode 2: a = lrelu(aff(up2(x)))       (final block: upsample -> BN -> LeakyReLU, models.py:52-54)
 // ---------------------------------------------------------------------------------------------
+// Channel-group-stationary: a thread keeps the affine parameters of its 8 channels (of ONE sample: blockIdx.y) in
+// registers and walks over output pixels, so the per-element work is one 16-byte load (four for the bilinear modes)
+// and one or two 16-byte stores.
 __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ mean_rstd,
                               const float* __restrict__ scale_ptr, const float* __restrict__ shift_ptr, int row_stride,
                               const int* __restrict__ cls, float slope, int mode, bf16* __restrict__ out_a,
-                              bf16* __restrict__ out_xu, int B, int H, int W, int cg) {
+                              bf16* __restrict__ out_xu, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = mode ? 2 * H : H, OW = mode ? 2 * W : W;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
-  const int ow = (int)(t % OW);
-  t /= OW;
-  const int oh = (int)(t % OH);
-  const int b = (int)(t / OH);
+  const int b = blockIdx.y;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  if (pr >= prows) return;
   const int row = cls != nullptr ? cls[b] : 0;
   float sc[8], sf[8];
 #pragma unroll
@@ -188,44 +188,49 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
     sc[j] = s;
     sf[j] = shift_ptr[(size_t)row * row_stride + ch] - mean_rstd[ch] * s;
   }
-  float v[8];
-  if (mode == 0) {
-    ld8(x + idx * 8, v);
+  const int npix = OH * OW;
+  const size_t in_base = (size_t)b * H * W, out_base = (size_t)b * npix;
+  const float shs = mode ? (float)(H - 1) / (float)(OH - 1) : 0.f, sws = mode ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
+    float v[8];
+    const size_t o = ((out_base + p) * cg + c) * 8;
+    if (mode == 0) {
+      ld8(x + o, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = lrelu_f(v[j] * sc[j] + sf[j], slope);
-    st8(out_a + idx * 8, v);
-    return;
-  }
-  const float shs = (float)(H - 1) / (float)(OH - 1), sws = (float)(W - 1) / (float)(OW - 1);
-  const Lerp Lh = lerp_src(oh, H, shs), Lw = lerp_src(ow, W, sws);
-  float q[4][8];
-  const size_t base = (size_t)b * H * W;
-  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i0) * cg + c) * 8, q[0]);
-  ld8(x + ((base + (size_t)Lh.i0 * W + Lw.i1) * cg + c) * 8, q[1]);
-  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i0) * cg + c) * 8, q[2]);
-  ld8(x + ((base + (size_t)Lh.i1 * W + Lw.i1) * cg + c) * 8, q[3]);
-  if (out_xu != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
-    st8(out_xu + idx * 8, v);
-  }
-  if (mode == 1) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[k][j] = lrelu_f(q[k][j] * sc[j] + sf[j], slope);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float u = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
-      v[j] = lrelu_f(u * sc[j] + sf[j], slope);
+      for (int j = 0; j < 8; ++j) v[j] = lrelu_f(v[j] * sc[j] + sf[j], slope);
+      st8(out_a + o, v);
+      continue;
     }
+    const int oh = p / OW, ow = p % OW;
+    const Lerp Lh = lerp_src(oh, H, shs), Lw = lerp_src(ow, W, sws);
+    float q[4][8];
+    ld8(x + ((in_base + (size_t)Lh.i0 * W + Lw.i0) * cg + c) * 8, q[0]);
+    ld8(x + ((in_base + (size_t)Lh.i0 * W + Lw.i1) * cg + c) * 8, q[1]);
+    ld8(x + ((in_base + (size_t)Lh.i1 * W + Lw.i0) * cg + c) * 8, q[2]);
+    ld8(x + ((in_base + (size_t)Lh.i1 * W + Lw.i1) * cg + c) * 8, q[3]);
+    const float w00 = Lh.w0 * Lw.w0, w01 = Lh.w0 * Lw.w1, w10 = Lh.w1 * Lw.w0, w11 = Lh.w1 * Lw.w1;
+    if (out_xu != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+      st8(out_xu + o, v);
+    }
+    (void)w00; (void)w01; (void)w10; (void)w11;
+    if (mode == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[k][j] = lrelu_f(q[k][j] * sc[j] + sf[j], slope);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
+        v[j] = lrelu_f(u * sc[j] + sf[j], slope);
+      }
+    }
+    st8(out_a + o, v);
   }
-  st8(out_a + idx * 8, v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,39 +352,48 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ x,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                     int row_stride, const int* __restrict__ cls, const float* __restrict__ M,
-                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int B, int H, int W, int cg,
+                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int H, int W, int cg,
                                     int x_up2) {
   const int C = cg * 8;
   const int OH = x_up2 ? 2 * H : H, OW = x_up2 ? 2 * W : W;
-  const long long HW = (long long)OH * OW;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * HW * cg) return;
-  const int c = (int)(idx % cg);
-  const int b = (int)(idx / (HW * cg));
+  const int b = blockIdx.y;
+  const int c = threadIdx.x % cg;
+  const int pr = threadIdx.x / cg;
+  const int prows = blockDim.x / cg;
+  if (pr >= prows) return;
   const int row = cls != nullptr ? cls[b] : 0;
-  float g[8], xv[8], o[8];
-  ld8(gy + idx * 8, g);
-  if (x_up2) {
-    const long long p = (idx / cg) % HW;
-    up2_load(x, b, (int)(p / OW), (int)(p % OW), H, W, cg, c, (float)(H - 1) / (float)(OH - 1),
-             (float)(W - 1) / (float)(OW - 1), xv);
-  } else {
-    ld8(x + idx * 8, xv);
-  }
+  float mu[8], rs[8], sc[8], m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = c * 8 + j;
-    const float r = mean_rstd[C + ch];
-    const float xh = (xv[j] - mean_rstd[ch]) * r;
-    o[j] = r * (scale_ptr[(size_t)row * row_stride + ch] * g[j] - M[ch] - xh * M[C + ch]);
+    mu[j] = mean_rstd[ch];
+    rs[j] = mean_rstd[C + ch];
+    sc[j] = scale_ptr[(size_t)row * row_stride + ch];
+    m1[j] = M[ch];
+    m2[j] = M[C + ch];
   }
-  if (residual != nullptr) {
-    float rv[8];
-    ld8(residual + idx * 8, rv);
+  const int npix = OH * OW;
+  const size_t base = (size_t)b * npix;
+  const float shs = x_up2 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sws = x_up2 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
+    const size_t off = ((base + p) * cg + c) * 8;
+    float g[8], xv[8], o[8];
+    ld8(gy + off, g);
+    if (x_up2) up2_load(x, b, p / OW, p % OW, H, W, cg, c, shs, sws, xv);
+    else ld8(x + off, xv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] += rv[j];
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv[j] - mu[j]) * rs[j];
+      o[j] = rs[j] * (sc[j] * g[j] - m1[j] - xh * m2[j]);
+    }
+    if (residual != nullptr) {
+      float rv[8];
+      ld8(residual + off, rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += rv[j];
+    }
+    st8(gx + off, o);
   }
-  st8(gx + idx * 8, o);
 }
 
 // plain transposed bilinear x2 (align_corners=True): g_lo = up2^T(g_hi)  (skip path of the generator block)
@@ -471,10 +485,17 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
   SPYR_C8(C);
   SPYR_REQUIRE(mode >= 0 && mode <= 2, "bn_act: bad mode %d", mode);
   SPYR_REQUIRE(mode == 0 || (H > 1 && W > 1), "bn_act: upsampling needs H,W > 1");
-  const long long n = (long long)B * H * W * (mode ? 4 : 1) * (C / 8);
-  bn_act_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr,
-                                                                          row_stride, cls, slope, mode, (bf16*)out_a,
-                                                                          (bf16*)out_xu, B, H, W, C / 8);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 256, "bn_act: C=%d too large", C);
+  const Threads t = pick_threads(cg, 256);
+  const int npix = H * W * (mode ? 4 : 1);
+  int gx = (npix + t.prows * 4 - 1) / (t.prows * 4);
+  const int cap = (2368 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  bn_act_kernel<<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr,
+                                                                     row_stride, cls, slope, mode, (bf16*)out_a,
+                                                                     (bf16*)out_xu, H, W, cg);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -515,10 +536,17 @@ extern "C" int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mea
                                  int row_stride, const int* cls, const float* M, const void* residual, void* gx, int B,
                                  int H, int W, int C, int x_up2, void* stream) {
   SPYR_C8(C);
-  const long long n = (long long)B * H * W * (C / 8) * (x_up2 ? 4 : 1);
-  bn_bwd_apply_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, B, H, W,
-      C / 8, x_up2);
+  const int cg = C / 8;
+  SPYR_REQUIRE(cg <= 256, "bn_bwd_apply: C=%d too large", C);
+  const Threads t = pick_threads(cg, 256);
+  const int npix = H * W * (x_up2 ? 4 : 1);
+  int gxx = (npix + t.prows * 4 - 1) / (t.prows * 4);
+  const int cap = (2368 + B - 1) / B;
+  if (gxx > cap) gxx = cap;
+  if (gxx < 1) gxx = 1;
+  bn_bwd_apply_kernel<<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg,
+      x_up2);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -182,7 +182,9 @@ __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, con
   }
 }
 
-constexpr int BT = 32;  // backward tile: 32 rows (cout) x 32 input channels x taps
+constexpr int BT = 32;  // backward tile: 32 rows (cout) x BTC input channels x taps
+// single-tap layers (linear, 1x1, embedding) take 9x wider tiles so that every CTA moves the same ~9K elements
+__host__ __device__ inline int sn_btc(int taps) { return taps == 1 ? 9 * BT : BT; }
 
 // pass 1: dots[l] += sum G * W      pass 2: out = (G - dots/sigma * u v^T) / sigma
 template <int PASS>
@@ -195,9 +197,10 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
   const spyr_sn_layer L = tab[l];
   if (L.gw_off < 0) return;
   const int tile = blockIdx.x - L.tile0_bwd;
-  const int ctiles = (L.cin + BT - 1) / BT;
-  const int co0 = (tile / ctiles) * BT, ci0 = (tile % ctiles) * BT;
-  const int nco = min(BT, L.rows - co0), nci = min(BT, L.cin - ci0);
+  const int btc = sn_btc(L.taps);
+  const int ctiles = (L.cin + btc - 1) / btc;
+  const int co0 = (tile / ctiles) * BT, ci0 = (tile % ctiles) * btc;
+  const int nco = min(BT, L.rows - co0), nci = min(btc, L.cin - ci0);
   const float* gw = gw_arena + L.gw_off;
   const int taps = L.taps;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -205,13 +208,13 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
     // coalesced along cout
     for (int r = wid; r < taps * nci; r += nw) {
       const int t = r / nci, ci = r % nci;
-      if (lane < nco) gsh[(t * BT + ci) * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
+      if (lane < nco) gsh[(t * btc + ci) * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
     }
   } else {
     for (int r = wid; r < nco; r += nw)
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e % taps;
-        gsh[(t * BT + ci) * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
+        gsh[(t * btc + ci) * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
       }
   }
   __syncthreads();
@@ -223,7 +226,7 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
       const float* wrow = L.w + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e % taps;
-        acc += gsh[(t * BT + ci) * (BT + 1) + r] * wrow[e];
+        acc += gsh[(t * btc + ci) * (BT + 1) + r] * wrow[e];
       }
     }
     acc = block_sum(acc, red);
@@ -238,7 +241,7 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
       const float* vv = sv + 1 + L.rows + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e % taps;
-        orow[e] = (gsh[(t * BT + ci) * (BT + 1) + r] - ur * vv[e]) * inv;
+        orow[e] = (gsh[(t * btc + ci) * (BT + 1) + r] - ur * vv[e]) * inv;
       }
     }
   }
@@ -262,7 +265,7 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     L.tile0_pack = t_pack;
     t_pack += L.pack_cin > 0 ? L.rows : 1;
     L.tile0_bwd = t_bwd;
-    t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, BT);
+    t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, sn_btc(L.taps));
     L.scratch_off = scratch;  // 16-byte aligned so the power-iteration vector can be read as float4
     scratch += (L.cols + L.rows + 3) & ~3;
     L.saved_off = saved;
