@@ -256,6 +256,8 @@ typedef struct {
   float* v[SPYR_ADAM_MAX_TENSORS];
   long long n[SPYR_ADAM_MAX_TENSORS];
 } spyr_adam_chunk;
+/* dst += src over a flat FP32 buffer (accumulating a second backward pass into the gradient arena of the first) */
+int spyr_add_inplace(float* dst, const float* src, long long n, void* stream);
 int spyr_adam_tick(int* step, void* stream);
 int spyr_adam_step(const spyr_adam_chunk* chunk, const int* step, float lr, float beta1, float beta2, float eps, void* stream);
 

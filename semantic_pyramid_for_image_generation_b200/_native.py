@@ -110,6 +110,7 @@ _SIGNATURES = {
     "spyr_rec_vec_bwd": [P, P, P, c_int, c_int, P, P, P],
     "spyr_diversity_fwd": [P, c_ll, P, c_ll, P, P, P],
     "spyr_diversity_bwd": [P, c_ll, P, P, P, P],
+    "spyr_add_inplace": [P, P, c_ll, P],
     "spyr_adam_tick": [P, P],
     "spyr_adam_step": [C.POINTER(AdamChunk), P, c_float, c_float, c_float, c_float, P],
 }

@@ -256,13 +256,39 @@ __global__ void adam_kernel(const spyr_adam_chunk args, const int* __restrict__ 
   const float bc1 = 1.f - powf(beta1, st);
   const float bc2s = sqrtf(1.f - powf(beta2, st));
   const float step_size = lr / bc1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n >> 2 : 0;
+  for (long long i = tid; i < n4; i += nthreads) {
+    const float4 gi = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(p)[i];
+#define SPYR_ADAM1(c)                                        \
+  mi.c = beta1 * mi.c + (1.f - beta1) * gi.c;                \
+  vi.c = beta2 * vi.c + (1.f - beta2) * gi.c * gi.c;         \
+  pi.c -= step_size * mi.c / (sqrtf(vi.c) / bc2s + eps);
+    SPYR_ADAM1(x) SPYR_ADAM1(y) SPYR_ADAM1(z) SPYR_ADAM1(w)
+#undef SPYR_ADAM1
+    reinterpret_cast<float4*>(m)[i] = mi;
+    reinterpret_cast<float4*>(v)[i] = vi;
+    reinterpret_cast<float4*>(p)[i] = pi;
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += nthreads) {
     const float gi = g[i];
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
     p[i] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
   }
 }
 
@@ -367,10 +393,20 @@ extern "C" int spyr_adam_step(const spyr_adam_chunk* chunk, const int* step, flo
   SPYR_REQUIRE(chunk && chunk->count > 0 && chunk->count <= SPYR_ADAM_MAX_TENSORS, "adam_step: bad chunk");
   long long maxn = 0;
   for (int i = 0; i < chunk->count; ++i) maxn = chunk->n[i] > maxn ? chunk->n[i] : maxn;
-  long long want = (maxn + 1023) / 1024;
-  const int gx = (int)(want < 1 ? 1 : (want > 148 ? 148 : want));
+  long long want = (maxn + 2047) / 2048;
+  const int gx = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
   dim3 grid(gx, chunk->count);
   adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*chunk, step, lr, beta1, beta2, eps);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_add_inplace(float* dst, const float* src, long long n, void* stream) {
+  SPYR_REQUIRE(dst && src && n % 4 == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0,
+               "add_inplace: needs 16-byte aligned buffers and n %% 4 == 0");
+  long long want = (n / 4 + 1023) / 1024;
+  const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  add_inplace_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, src, n / 4);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

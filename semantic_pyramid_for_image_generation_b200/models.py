@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import engine, vgg_engine
+from ._native import call
 from .engine import GradArena
 from .spectral import LayerSpec, SNSet, SpectralNormHolder
 
@@ -212,11 +213,18 @@ class _DiscriminatorFn(torch.autograd.Function):
         needs = ctx.needs_input_grad[3:]
         grad, g_img = engine.discriminator_backward(module, ctx.c, g_out, any(needs), ctx.needs_input_grad[1])
         ctx.c = None
+        pg = [None] * len(needs)
         if grad is not None:
-            module._last_grad_arena = grad
-            pg = module._ga.views(grad, needs)
-        else:
-            pg = [None] * len(needs)
+            ga, prev = module._ga, module._last_grad_arena
+            p0 = ga.params[0]
+            if all(needs) and prev is not None and p0.grad is not None and prev.device == grad.device and \
+                    p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]:
+                # second backward pass of an accumulation window (D(real) + D(fake), model_wrapper.py:153-160): every
+                # .grad is a view of the previous arena, so one flat add replaces 56 per-parameter accumulations
+                call("spyr_add_inplace", prev.data_ptr(), grad.data_ptr(), grad.numel())
+            else:
+                module._last_grad_arena = grad
+                pg = module._ga.views(grad, needs)
         return (None, g_img, None) + tuple(pg)
 
 
