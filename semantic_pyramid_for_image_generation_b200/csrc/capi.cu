@@ -49,7 +49,8 @@ int spyr_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(gptr), gdims, gstr, gbox,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : (swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     spyr_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,

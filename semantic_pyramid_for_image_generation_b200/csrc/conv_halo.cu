@@ -23,6 +23,8 @@
 // 16x8 stay on the conv_tc.cu kernel.
 #include "common.cuh"
 #include "../../include/spyramid_b200.h"
+#include <cstdlib>
+
 #include "conv_halo_common.cuh"
 
 extern void spyr_count_launch();
@@ -35,11 +37,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + A_BUFS * p.a_buf_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + p.b_stages * p.b_stage_bytes);
+  uint8_t* b_ring = smem + p.a_bufs * p.a_buf_bytes;
+  uint8_t* epi_stage = b_ring + p.b_stages * p.b_stage_bytes;  // EPI_STAGE_TOTAL bytes when p.tma_store
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (p.tma_store ? EPI_STAGE_TOTAL : 0));
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + A_BUFS;
-  uint64_t* b_full = a_empty + A_BUFS;
+  uint64_t* a_empty = a_full + p.a_bufs;
+  uint64_t* b_full = a_empty + p.a_bufs;
   uint64_t* b_empty = b_full + p.b_stages;
   uint64_t* acc_full = b_empty + p.b_stages;
   uint64_t* acc_empty = acc_full + 2;
@@ -54,9 +57,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       tma_prefetch_desc(&maps.x[s]);
       tma_prefetch_desc(&maps.w[s]);
     }
+    if (p.tma_store) {
+      tma_prefetch_desc(&maps.y[0]);
+      tma_prefetch_desc(&maps.y[1]);
+    }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < A_BUFS; ++i) {
+    for (int i = 0; i < p.a_bufs; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
@@ -82,10 +89,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   const int th_rows = 16 * p.msub;
 
   if (warp == 0) {
-    if (elect_one()) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer: warp-uniform coordinates, one elected lane issues =====
+      const bool issue = elect_one();
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
+      bool load_b = true;  // resident weights: only the first tile of this CTA loads them
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
         const int w0 = (m_tile % p.tiles_w) * 8;
@@ -97,23 +106,27 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           const int taps = bd ? 9 : 1;
           for (int c = 0; c < p.kchunks[s]; ++c) {
             mbar_wait(&a_empty[abuf], aph ^ 1);
-            mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(p.a_rows[s] * 128));
-            tma_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
-            if (++abuf == A_BUFS) {
+            if (issue) {
+              mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(p.a_rows[s] * 128));
+              tma_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
+            }
+            if (++abuf == p.a_bufs) {
               abuf = 0;
               aph ^= 1;
             }
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap = 0; load_b && tap < taps; ++tap) {
               mbar_wait(&b_empty[bst], bph ^ 1);
               uint8_t* b_dst = b_ring + bst * p.b_stage_bytes;
-              if (p.wmn[s]) {
-                mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(b_chunks * 8192));
-                const int wtap = p.wpi[s] ? n0 : (bd ? 8 - tap : 0);
-                for (int j = 0; j < b_chunks; ++j)
-                  tma_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
-              } else {
-                mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
-                tma_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
+              if (issue) {
+                if (p.wmn[s]) {
+                  mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(b_chunks * 8192));
+                  const int wtap = p.wpi[s] ? n0 : (bd ? 8 - tap : 0);
+                  for (int j = 0; j < b_chunks; ++j)
+                    tma_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
+                } else {
+                  mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
+                  tma_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
+                }
               }
               if (++bst == p.b_stages) {
                 bst = 0;
@@ -122,13 +135,20 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
             }
           }
         }
+        if (p.b_resident) load_b = false;
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: ONE thread runs the whole loop.  Descriptors are 64-bit integers advanced by plain adds on the
-    // 14-bit start-address field (16-byte units); recomputing them per MMA made this thread, not the tensor pipe, the
-    // bottleneck (ncu: 22 dependent instructions per tcgen05.mma).
-    if (lane == 0) {
+    // ===== MMA issuer.  The whole warp runs the loop with warp-uniform operands, only the tcgen05 instructions are
+    // predicated on one elected lane: the descriptors then live in uniform registers and each UTCHMMA costs one or two
+    // uniform adds.  (A loop run by `lane == 0` alone compiles every MMA into an R2UR + ELECT + branch waterfall,
+    // ~12 instructions, which capped N=64 layers at 130 clk per MMA against a tensor-pipe floor of 75:
+    // tests/native/mma_probe.cu.)  Descriptors are 64-bit integers advanced by plain adds on the 14-bit start-address
+    // field (16-byte units).
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
       const uint32_t idesc_k = umma_idesc_bf16(128, p.block_n, 0, 0);
       const uint32_t idesc_mn = umma_idesc_bf16(128, p.block_n, 0, 1);
       const uint64_t desc_base = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // version 1, SWIZZLE_128B
@@ -162,36 +182,42 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
             const uint32_t a_lo = a_ring_lo + (uint32_t)abuf * a_buf16;
             uint32_t row0 = 0;  // halo row of output pixel (0,0) for the current tap: dy*10 + dx
             for (int tap = 0; tap < taps; ++tap) {
-              mbar_wait(&b_full[bst], bph);
+              if (!p.b_resident)
+                mbar_wait(&b_full[bst], bph);
+              else if (it == 0)
+                mbar_wait(&b_full[bst], 0);
               tc_fence_after();
               const uint64_t db0 = b_hi | (uint64_t)(b_ring_lo + (uint32_t)bst * b_stage16);
               const uint64_t da0 = a_hi | (uint64_t)(a_lo + row0 * row16);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                umma_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
-              if (p.msub == 2) {
+              if (leader) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  umma_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k), idesc,
-                            k == 0 ? accum : 1u);
+                  umma_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
+                if (p.msub == 2) {
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k),
+                              idesc, k == 0 ? accum : 1u);
+                }
+                if (!p.b_resident) umma_commit(&b_empty[bst]);
               }
               accum = 1;
-              umma_commit(&b_empty[bst]);
               if (++bst == p.b_stages) {
                 bst = 0;
                 bph ^= 1;
               }
               row0 += ((tap % 3) == 2) ? 8u : 1u;  // dx wraps: next halo row block (10 - 2)
             }
-            umma_commit(&a_empty[abuf]);
-            if (++abuf == A_BUFS) {
+            if (leader) umma_commit(&a_empty[abuf]);
+            if (++abuf == p.a_bufs) {
               abuf = 0;
               aph ^= 1;
             }
           }
         }
-        umma_commit(&acc_full[buf]);
+        if (leader) umma_commit(&acc_full[buf]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
@@ -201,6 +227,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
     int it = 0;
     int staged_n_off = -1, cbuf = 1;
+    int sbuf = 0;
+    EpiStore es;
+    es.maps = p.tma_store ? maps.y : nullptr;
+    es.stage = smem_u32(epi_stage) + (uint32_t)((warp - 4) * 2 * EPI_STAGE_BYTES);
+    es.lane = lane;
+    es.sbuf = &sbuf;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -259,17 +291,21 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
         const int h = h0 + sub * 16 + (m >> 3);
         const size_t pix = ((size_t)n * p.H + h) * p.W + w;
         const uint32_t acc = tmem_base + (uint32_t)((buf * p.msub + sub) * p.bn_cols) + ((uint32_t)(q * 32) << 16);
+        es.w = w0;
+        es.h = h0 + sub * 16 + q * 4;
+        es.n = n;
         for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_chunk(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub]);
+          epilogue_dispatch(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();  // staged chunks must be read (and written out) before the CTA exits
   }
 
   tc_fence_before();
@@ -318,6 +354,7 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.n_tiles = ceil_div(d->Cout, bn);
   p.total_tiles = p.m_tiles * p.n_tiles;
   HaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
   int max_rows = 0;
   p.b_stage_bytes = bn * 128;
   for (int s = 0; s < d->nsrc; ++s) {
@@ -360,12 +397,47 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     maps.w[s] = maps.w[0];
   }
   p.a_buf_bytes = ceil_div(max_rows * 128, 1024) * 1024;
-  const int budget = 200 * 1024 - A_BUFS * p.a_buf_bytes;
-  int stages = budget / p.b_stage_bytes;
-  if (stages > 12) stages = 12;
-  if (d->stages > 0 && d->stages < stages) stages = d->stages;
-  if (stages < 2) return -1;
+  // Shared-memory plan (218 KB usable next to barriers, epilogue constants and alignment slack).  If every weight slice
+  // of the layer fits beside two halo tiles they are loaded once per CTA and stay resident (64-channel layers: 72 KB
+  // instead of 73 KB of L2->SMEM traffic per tile); otherwise they stream through a ring of up to 12 stages.  What is
+  // left deepens the halo ring (thin, HBM-bound 1x1 layers need > 2 tiles in flight to cover the memory latency).
+  // Opt-in experiment: on B200 the staged TMA store measured no faster than 256-bit per-thread stores (the epilogue was
+  // instruction-latency bound, not L1-wavefront bound) and costs 32 KB of shared memory.
+  static const bool use_tma_store = getenv("SPYR_CONV_TMA_STORE") != nullptr;
+  p.tma_store = (d->y_f32 == nullptr && (d->y_raw != nullptr || d->y_act != nullptr) && use_tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t strides[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->W * d->Cout * 2, (uint64_t)d->H * d->W * d->Cout * 2};
+    uint32_t box[4] = {32, 8, 4, 1};
+    const void* y0 = d->y_raw != nullptr ? d->y_raw : d->y_act;
+    const void* y1 = d->y_act != nullptr ? d->y_act : d->y_raw;
+    SPYR_REQUIRE(((uintptr_t)y0 & 15) == 0 && ((uintptr_t)y1 & 15) == 0, "conv2d_fprop: unaligned output pointer");
+    if (spyr_tmap_encode(&maps.y[0], y0, 4, dims, strides, box, 2)) return 3;
+    if (spyr_tmap_encode(&maps.y[1], y1, 4, dims, strides, box, 2)) return 3;
+  } else {
+    maps.y[0] = maps.x[0];
+    maps.y[1] = maps.x[0];
+  }
+  const int usable = 218 * 1024 - 2 * 11 * bn * 4 - (p.tma_store ? EPI_STAGE_TOTAL : 0);
+  int stages_per_tile = 0;
+  for (int s = 0; s < d->nsrc; ++s) stages_per_tile += p.kchunks[s] * (p.border[s] ? 9 : 1);
+  int stages;
+  p.b_resident = (p.n_tiles == 1 && stages_per_tile <= 24 && d->stages == 0 &&
+                  stages_per_tile * p.b_stage_bytes + 2 * p.a_buf_bytes <= usable) ? 1 : 0;
+  for (int s = 0; s < d->nsrc; ++s)
+    if (p.wpi[s]) p.b_resident = 0;  // per-image weights change with the tile
+  if (p.b_resident) {
+    stages = stages_per_tile;
+  } else {
+    stages = (usable - 18 * 1024 - 2 * p.a_buf_bytes) / p.b_stage_bytes;
+    if (stages > 12) stages = 12;
+    if (d->stages > 0 && d->stages < stages) stages = d->stages;
+    if (stages < 2) return -1;
+  }
   p.b_stages = stages;
+  p.a_bufs = (usable - stages * p.b_stage_bytes) / p.a_buf_bytes;
+  if (p.a_bufs > 4) p.a_bufs = 4;
+  if (p.a_bufs < 2) p.a_bufs = 2;
   p.bias = d->bias; p.bias2 = d->bias2; p.bias3 = d->bias3;
   p.stencil_mask = d->stencil_mask; p.stencil_w = d->stencil_w;
   p.dmask = (const bf16*)d->dmask; p.dmask_slope = d->dmask_slope;
@@ -373,8 +445,11 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.y_raw = (bf16*)d->y_raw; p.y_act = (bf16*)d->y_act;
   p.act = d->act; p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
-  const size_t smem_bytes = (size_t)A_BUFS * p.a_buf_bytes + (size_t)stages * p.b_stage_bytes +
-                            (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
+  p.epi_mode = epi_mode_for(p);
+  const size_t smem_bytes = (size_t)p.a_bufs * p.a_buf_bytes + (size_t)stages * p.b_stage_bytes +
+                            (size_t)(p.tma_store ? EPI_STAGE_TOTAL : 0) +
+                            (2 * p.a_bufs + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
+  SPYR_REQUIRE(smem_bytes <= 227 * 1024, "conv2d_fprop: shared-memory plan of %zu bytes exceeds 227 KB", smem_bytes);
   static bool configured = false;
   if (!configured) {
     SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -17,6 +17,8 @@
 //     (CTA 1 through mapa + mbarrier.arrive.shared::cluster).
 #include "common.cuh"
 #include "../../include/spyramid_b200.h"
+#include <cstdlib>
+
 #include "conv_halo_common.cuh"
 
 extern void spyr_count_launch();
@@ -141,8 +143,10 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   const int total_pairs = (p.m_tiles >> 1) * p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (both CTAs): own halo tiles, own half of every weight slice =====
+    {
+      // ===== TMA producer (both CTAs): own halo tiles, own half of every weight slice; warp-uniform coordinates,
+      // one elected lane issues =====
+      const bool issue = elect_one();
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = pair; t < total_pairs; t += num_pairs) {
@@ -157,8 +161,10 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           const int taps = bd ? 9 : 1;
           for (int c = 0; c < p.kchunks[s]; ++c) {
             mbar_wait(&a_empty[abuf], aph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(2 * p.a_rows[s] * 128));
-            tma2_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
+            if (issue) {
+              if (leader) mbar_arrive_expect_tx(&a_full[abuf], (uint32_t)(2 * p.a_rows[s] * 128));
+              tma2_load_4d(a_ring + abuf * p.a_buf_bytes, &maps.x[s], &a_full[abuf], c * KC, w0 - bd, h0 - bd, n0);
+            }
             if (++abuf == A_BUFS) {
               abuf = 0;
               aph ^= 1;
@@ -166,13 +172,15 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[bst], bph ^ 1);
               uint8_t* b_dst = b_ring + bst * p.b_stage_bytes;
-              if (leader) mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
-              if (p.wmn[s]) {
-                const int wtap = p.wpi[s] ? n0 : (bd ? 8 - tap : 0);
-                for (int j = 0; j < (half_n >> 6); ++j)
-                  tma2_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
-              } else {
-                tma2_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
+              if (issue) {
+                if (leader) mbar_arrive_expect_tx(&b_full[bst], (uint32_t)(p.block_n * 128));
+                if (p.wmn[s]) {
+                  const int wtap = p.wpi[s] ? n0 : (bd ? 8 - tap : 0);
+                  for (int j = 0; j < (half_n >> 6); ++j)
+                    tma2_load_3d(b_dst + j * 8192, &maps.w[s], &b_full[bst], n_off + j * 64, c * KC, wtap);
+                } else {
+                  tma2_load_3d(b_dst, &maps.w[s], &b_full[bst], c * KC, n_off, p.wpi[s] ? n0 : tap);
+                }
               }
               if (++bst == p.b_stages) {
                 bst = 0;
@@ -182,10 +190,14 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
+    if (leader) {
+      // ===== MMA issuer: the leader CTA's warp 1 drives both SMs.  Warp-uniform operands, one elected lane issues
+      // (see conv_halo.cu: a single-lane loop costs an R2UR/ELECT waterfall per MMA) =====
+      const bool issue = elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
       const uint32_t idesc_k = umma_idesc_bf16(256, p.block_n, 0, 0);
       const uint32_t idesc_mn = umma_idesc_bf16(256, p.block_n, 0, 1);
       const uint64_t desc_base = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -222,32 +234,35 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
               tc_fence_after();
               const uint64_t db0 = b_hi | (uint64_t)(b_ring_lo + (uint32_t)bst * b_stage16);
               const uint64_t da0 = a_hi | (uint64_t)(a_lo + row0 * 8u);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                umma2_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
-              if (p.msub == 2) {
+              if (issue) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  umma2_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k), idesc,
-                             k == 0 ? accum : 1u);
+                  umma2_bf16(acc0, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, k == 0 ? accum : 1u);
+                if (p.msub == 2) {
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma2_bf16(acc0 + (uint32_t)p.bn_cols, da0 + (uint64_t)(sub16 + 2 * k), db0 + (uint64_t)(bk16 * k),
+                               idesc, k == 0 ? accum : 1u);
+                }
+                umma2_commit_mc(&b_empty[bst]);
               }
               accum = 1;
-              umma2_commit_mc(&b_empty[bst]);
               if (++bst == p.b_stages) {
                 bst = 0;
                 bph ^= 1;
               }
               row0 += ((tap % 3) == 2) ? 8u : 1u;
             }
-            umma2_commit_mc(&a_empty[abuf]);
+            if (issue) umma2_commit_mc(&a_empty[abuf]);
             if (++abuf == A_BUFS) {
               abuf = 0;
               aph ^= 1;
             }
           }
         }
-        umma2_commit_mc(&acc_full[buf]);
+        if (issue) umma2_commit_mc(&acc_full[buf]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue (both CTAs, own TMEM rows = own pixel tile, all block_n columns) =====
@@ -257,6 +272,13 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     const int et = threadIdx.x - 128;
     int it = 0;
     int staged_n_off = -1, cbuf = 1;
+    int sbuf = 0;
+    EpiStore es;
+    es.maps = nullptr;  // per-thread stores (TMA-store epilogue: conv_halo.cu only so far)
+    es.stage = 0;
+    es.lane = lane;
+    es.sbuf = &sbuf;
+    es.w = es.h = es.n = 0;
     for (int t = pair; t < total_pairs; t += num_pairs, ++it) {
       const int buf = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -319,7 +341,7 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_chunk(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub]);
+          epilogue_dispatch(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
@@ -355,7 +377,8 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.nsrc = d->nsrc;
-  const int bn = (d->Cout % 256 == 0) ? 256 : 128;  // whole N blocks only (e.g. 384 = 3 x 128)
+  static const bool bn128 = getenv("SPYR_PAIR_BN128") != nullptr;  // experiment: less weight traffic per FLOP
+  const int bn = (d->Cout % 256 == 0 && !(bn128 && d->H % 32 == 0)) ? 256 : 128;  // whole N blocks only (384 = 3 x 128)
   p.msub = (d->H % 32 == 0 && bn <= 128) ? 2 : 1;
   p.block_n = bn;
   p.bn_cols = bn;
@@ -423,6 +446,7 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.y_raw = (bf16*)d->y_raw; p.y_act = (bf16*)d->y_act;
   p.act = d->act; p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
+  p.epi_mode = epi_mode_for(p);
   const size_t smem_bytes = (size_t)A_BUFS * p.a_buf_bytes + (size_t)stages * p.b_stage_bytes +
                             (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
   static bool configured = false;

@@ -22,6 +22,10 @@ struct HaloParams {
   int a_rows[3];   // rows (pixels) of the A box of this source
   int block_n, bn_cols;  // bn_cols: TMEM column stride of one accumulator (power of two >= 32)
   int a_buf_bytes, b_stage_bytes, b_stages;
+  int a_bufs;      // halo-tile ring depth (conv_halo.cu; the pair kernel uses A_BUFS)
+  int epi_mode;    // 0: generic epilogue_chunk, else a specialised epilogue_chunk_fast (epi_mode_for)
+  int tma_store;   // epilogue writes y_raw / y_act through shared-memory staging + TMA stores (maps.y)
+  int b_resident;  // conv_halo.cu: every (source, chunk, tap) weight slice of the layer stays in shared memory
   uint32_t tmem_cols;
   const float* bias;
   const float* bias2;
@@ -41,7 +45,41 @@ struct HaloParams {
 struct HaloMaps {
   CUtensorMap x[3];
   CUtensorMap w[3];
+  CUtensorMap y[2];  // y_raw, y_act as (C, W, H, B) with a (32 ch, 8, 4, 1) box, SWIZZLE_64B: epilogue TMA stores
 };
+
+constexpr int EPI_STAGE_BYTES = 2048;  // one warp's 32 pixels x 32 channels BF16
+constexpr int EPI_STAGE_TOTAL = EPI_WARPS * 2 * EPI_STAGE_BYTES;
+
+// Where one warp's 32x32 chunk goes when the epilogue stores through TMA: the warp's two staging buffers (1 KB aligned)
+// and the box coordinates.  A per-thread STG of this chunk touches 32 different 128-byte lines per request
+// (~53 L1 data-pipe wavefronts, ncu) and competes with the tensor pipe's operand fetch for the same pipe; staging the
+// chunk in shared memory (4 conflict-free STS.128 per thread) and letting the TMA engine write it costs ~4x fewer.
+struct EpiStore {
+  const CUtensorMap* maps;  // nullptr: per-thread global stores
+  uint32_t stage;           // shared address of this warp's staging buffers (2 x EPI_STAGE_BYTES)
+  int w, h, n;              // box origin (pixels) of this warp's 8 x 4 pixel block
+  int lane;
+  int* sbuf;                // which of the two buffers the next store uses
+};
+
+__device__ __forceinline__ void epi_tma_store(const EpiStore& es, const CUtensorMap* map, int col0, const uint32_t* o) {
+  const int b = *es.sbuf;
+  *es.sbuf = b ^ 1;
+  if (es.lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+  __syncwarp();
+  // row = lane (64 bytes), SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  const uint32_t row = es.stage + (uint32_t)b * EPI_STAGE_BYTES + (uint32_t)es.lane * 64u;
+  const uint32_t x = ((uint32_t)es.lane >> 1) & 3u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sts128(row + (((uint32_t)c ^ x) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (es.lane == 0) {
+    tma_store_4d(map, es.stage + (uint32_t)b * EPI_STAGE_BYTES, col0, es.w, es.h, es.n);
+    bulk_commit();
+  }
+}
 
 // Per-tile epilogue constants staged in shared memory by the epilogue warps: the summed bias vectors of this N block and
 // the ten FP32 stencil rows of the mask channel.  Every lane of a warp reads the same address (broadcast).
@@ -51,7 +89,7 @@ struct EpiConst {
 };
 
 __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32_t* r, size_t pix, int col0, int c0,
-                                               const EpiConst& ec, const float* mk, int mk_mode) {
+                                               const EpiConst& ec, const float* mk, int mk_mode, const EpiStore& es) {
   if (col0 >= p.Cout) return;
   if (p.y_f32 != nullptr) {
     float* dst = p.y_f32 + pix * p.Cout + col0;
@@ -68,19 +106,38 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
     return;
   }
   const size_t off0 = pix * p.Cout + col0;
+  const bool full = col0 + 32 <= p.Cout;
+  const bool wide = full && (p.Cout & 15) == 0;  // 32-byte aligned 16-channel groups -> 256-bit LDG/STG
   // issue every global read of this 32-channel chunk before any arithmetic (read-only path, independent of the stores)
-  uint4 dm[4], rs[4];
+  uint32_t dm[16], rs[16];
   if (p.dmask != nullptr) {
+    if (wide) {
+      ldg256(p.dmask + off0, dm);
+      ldg256(p.dmask + off0 + 16, dm + 8);
+    } else {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (col0 + g * 8 + 8 <= p.Cout) dm[g] = __ldg(reinterpret_cast<const uint4*>(p.dmask + off0 + g * 8));
+      for (int g = 0; g < 4; ++g)
+        if (col0 + g * 8 + 8 <= p.Cout) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.dmask + off0 + g * 8));
+          dm[4 * g] = u.x; dm[4 * g + 1] = u.y; dm[4 * g + 2] = u.z; dm[4 * g + 3] = u.w;
+        }
+    }
   }
   if (p.residual != nullptr) {
+    if (wide) {
+      ldg256(p.residual + off0, rs);
+      ldg256(p.residual + off0 + 16, rs + 8);
+    } else {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (col0 + g * 8 + 8 <= p.Cout) rs[g] = __ldg(reinterpret_cast<const uint4*>(p.residual + off0 + g * 8));
+      for (int g = 0; g < 4; ++g)
+        if (col0 + g * 8 + 8 <= p.Cout) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + off0 + g * 8));
+          rs[4 * g] = u.x; rs[4 * g + 1] = u.y; rs[4 * g + 2] = u.z; rs[4 * g + 3] = u.w;
+        }
+    }
   }
   const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
+  uint32_t oraw[16], oact[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = col0 + g * 8;
@@ -111,44 +168,148 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
       }
     }
     if (p.dmask != nullptr) {
-      const uint32_t mw[4] = {dm[g].x, dm[g].y, dm[g].z, dm[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(mw[j]);
+        const float2 f = unpack_bf16x2(dm[4 * g + j]);
         if (!(f.x > 0.f)) v[2 * j] *= p.dmask_slope;
         if (!(f.y > 0.f)) v[2 * j + 1] *= p.dmask_slope;
       }
     }
     if (p.residual != nullptr) {
-      const uint32_t rw[4] = {rs[g].x, rs[g].y, rs[g].z, rs[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(rw[j]);
+        const float2 f = unpack_bf16x2(rs[4 * g + j]);
         v[2 * j] += f.x;
         v[2 * j + 1] += f.y;
       }
     }
-    const size_t off = off0 + g * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oraw[4 * g + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oact[4 * g + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
+  if (es.maps != nullptr) {
+    // channels past Cout (ragged last chunk) hold garbage in o*: the TMA store clips them
+    if (p.y_raw != nullptr) epi_tma_store(es, &es.maps[0], col0, oraw);
+    if (p.y_act != nullptr) epi_tma_store(es, &es.maps[1], col0, oact);
+  } else if (wide) {
     if (p.y_raw != nullptr) {
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]);
-      o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]);
-      o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(p.y_raw + off) = o;
+      stg256(p.y_raw + off0, oraw);
+      stg256(p.y_raw + off0 + 16, oraw + 8);
     }
     if (p.y_act != nullptr) {
+      stg256(p.y_act + off0, oact);
+      stg256(p.y_act + off0 + 16, oact + 8);
+    }
+  } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]);
-      o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]);
-      o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(p.y_act + off) = o;
+    for (int g = 0; g < 4; ++g) {
+      if (col0 + g * 8 + 8 > p.Cout) break;
+      if (p.y_raw != nullptr)
+        *reinterpret_cast<uint4*>(p.y_raw + off0 + g * 8) = make_uint4(oraw[4 * g], oraw[4 * g + 1], oraw[4 * g + 2], oraw[4 * g + 3]);
+      if (p.y_act != nullptr)
+        *reinterpret_cast<uint4*>(p.y_act + off0 + g * 8) = make_uint4(oact[4 * g], oact[4 * g + 1], oact[4 * g + 2], oact[4 * g + 3]);
     }
   }
 }
 
+
+// ---- specialised epilogue: compile-time feature set, no branches inside the 32-channel chunk ----
+// The generic epilogue_chunk above tests every optional feature per 8-channel group; ncu counted ~375 warp instructions
+// per chunk (1.3 branches per FADD) executed serially by each of the 8 epilogue warps, which made the epilogue -- not the
+// tensor pipe -- the critical path of the 64-channel layers (7000 clk per 256-pixel tile against 5400 clk of MMAs).
+// OUT: 1 = y_raw, 2 = y_act, 3 = both.  Requires Cout % 32 == 0 (every chunk full, 32-byte aligned) and no stencil.
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int OUT, bool DMASK, bool RES>
+__device__ __forceinline__ void epilogue_chunk_fast(const HaloParams& p, const uint32_t* r, size_t off0, int col0,
+                                                    uint32_t bias_saddr, const EpiStore& es) {
+  uint32_t dm[16], rs[16];
+  if (DMASK) {
+    ldg256(p.dmask + off0, dm);
+    ldg256(p.dmask + off0 + 16, dm + 8);
+  }
+  if (RES) {
+    ldg256(p.residual + off0, rs);
+    ldg256(p.residual + off0 + 16, rs + 8);
+  }
+  const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
+  const float gs = p.dmask_slope;
+  uint32_t oraw[16], oact[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 b = lds128f(bias_saddr + q4 * 16);
+    float v[4] = {__uint_as_float(r[4 * q4]) + b.x, __uint_as_float(r[4 * q4 + 1]) + b.y,
+                  __uint_as_float(r[4 * q4 + 2]) + b.z, __uint_as_float(r[4 * q4 + 3]) + b.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float a = v[2 * h], c = v[2 * h + 1];
+      if (DMASK) {
+        const float2 f = unpack_bf16x2(dm[2 * q4 + h]);
+        a = f.x > 0.f ? a : a * gs;
+        c = f.y > 0.f ? c : c * gs;
+      }
+      if (RES) {
+        const float2 f = unpack_bf16x2(rs[2 * q4 + h]);
+        a += f.x;
+        c += f.y;
+      }
+      if (OUT & 1) oraw[2 * q4 + h] = pack_bf16x2(a, c);
+      if (OUT & 2) {
+        a = a > 0.f ? a : a * sl;
+        c = c > 0.f ? c : c * sl;
+        oact[2 * q4 + h] = pack_bf16x2(a, c);
+      }
+    }
+  }
+  if (es.maps != nullptr) {
+    if (OUT & 1) epi_tma_store(es, &es.maps[0], col0, oraw);
+    if (OUT & 2) epi_tma_store(es, &es.maps[1], col0, oact);
+  } else {
+    if (OUT & 1) {
+      stg256(p.y_raw + off0, oraw);
+      stg256(p.y_raw + off0 + 16, oraw + 8);
+    }
+    if (OUT & 2) {
+      stg256(p.y_act + off0, oact);
+      stg256(p.y_act + off0 + 16, oact + 8);
+    }
+  }
+}
+
+// epi_mode: 0 = generic; otherwise 1 + (OUT - 1) * 4 + DMASK * 2 + RES
+__host__ inline int epi_mode_for(const HaloParams& p) {
+  if (p.y_f32 != nullptr || p.stencil_mask != nullptr || p.stencil_w != nullptr || (p.Cout & 31) != 0) return 0;
+  const int out = (p.y_raw != nullptr ? 1 : 0) | (p.y_act != nullptr ? 2 : 0);
+  if (out == 0) return 0;
+  return 1 + (out - 1) * 4 + (p.dmask != nullptr ? 2 : 0) + (p.residual != nullptr ? 1 : 0);
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const HaloParams& p, const uint32_t* r, size_t pix, int col0, int c0,
+                                                  const EpiConst& ec, const float* mk, int mk_mode, const EpiStore& es) {
+  const size_t off0 = pix * p.Cout + col0;
+  const uint32_t bs = smem_u32(ec.bias + c0);
+  switch (p.epi_mode) {
+    case 1: epilogue_chunk_fast<1, false, false>(p, r, off0, col0, bs, es); break;
+    case 2: epilogue_chunk_fast<1, false, true>(p, r, off0, col0, bs, es); break;
+    case 3: epilogue_chunk_fast<1, true, false>(p, r, off0, col0, bs, es); break;
+    case 4: epilogue_chunk_fast<1, true, true>(p, r, off0, col0, bs, es); break;
+    case 5: epilogue_chunk_fast<2, false, false>(p, r, off0, col0, bs, es); break;
+    case 6: epilogue_chunk_fast<2, false, true>(p, r, off0, col0, bs, es); break;
+    case 7: epilogue_chunk_fast<2, true, false>(p, r, off0, col0, bs, es); break;
+    case 8: epilogue_chunk_fast<2, true, true>(p, r, off0, col0, bs, es); break;
+    case 9: epilogue_chunk_fast<3, false, false>(p, r, off0, col0, bs, es); break;
+    case 10: epilogue_chunk_fast<3, false, true>(p, r, off0, col0, bs, es); break;
+    case 11: epilogue_chunk_fast<3, true, false>(p, r, off0, col0, bs, es); break;
+    case 12: epilogue_chunk_fast<3, true, true>(p, r, off0, col0, bs, es); break;
+    default: epilogue_chunk(p, r, pix, col0, c0, ec, mk, mk_mode, es); break;
+  }
+}
 
 }  // namespace halo

@@ -168,6 +168,8 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
       // ===== MMA issuer =====
       const uint32_t idesc_k = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
       const uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 1);
+      const bool issue = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int s = 0, s_end = p.ktaps[0] * p.kchunks[0];
@@ -179,18 +181,19 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
         const bool mn = p.wmn[s] != 0;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + A_BYTES;
+        // warp-uniform operands, elected issue (a single-lane loop costs an R2UR/ELECT waterfall per MMA)
+        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint64_t da0 = umma_smem_desc_sw128(a_addr, 0, 1024);
+        // K-major B: 16 channels = 32 B along the swizzled row.  MN-major B: 16 k-rows of 128 B = 2 KB,
+        // 64-column chunks 8 KB apart (LBO), 8-row swizzle atoms 1 KB apart (SBO).
+        const uint64_t db0 = mn ? umma_smem_desc_sw128(b_addr, 8192, 1024) : umma_smem_desc_sw128(b_addr, 0, 1024);
+        const uint32_t bk16 = mn ? (2048u >> 4) : 2u;
+        const uint32_t idesc = mn ? idesc_mn : idesc_k;
+        if (issue) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            // K-major B: 16 channels = 32 B along the swizzled row.  MN-major B: 16 k-rows of 128 B = 2 KB,
-            // 64-column chunks 8 KB apart (LBO), 8-row swizzle atoms 1 KB apart (SBO).
-            const uint64_t db = mn ? umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                   : umma_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(tmem_base, da, db, mn ? idesc_mn : idesc_k, (it > k_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tmem_u, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(bk16 * k), idesc, (it > k_begin || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (it == k_end - 1) umma_commit(tmem_full_bar);
         }
@@ -462,8 +465,11 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         }
       }
     } else if (warp == 1) {
-      // one thread issues every MMA; descriptors advance by integer adds on the start-address field (16-byte units)
-      if (lane == 0) {
+      // warp-uniform operands, one elected lane issues; descriptors advance by integer adds on the start-address
+      // field (16-byte units)
+      {
+        const bool issue = elect_one();
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, 1, 1);
         const uint64_t hi = ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)((p.lbo >> 4) & 0x3FFF) << 16) |
                             ((uint64_t)((p.sbo >> 4) & 0x3FFF) << 32);
@@ -476,16 +482,19 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
           tc_fence_after();
           const uint64_t da0 = hi | (uint64_t)(base16 + (uint32_t)stage * stage16);
           const uint64_t db0 = da0 + a16;
+          if (issue) {
 #pragma unroll
-          for (int k = 0; k < KP / 16; ++k)  // 16 pixels (K) per MMA = 16 rows of 128 B = 2 KB
-            umma_bf16(tmem_base, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc, (it > k_begin || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (it == k_end - 1) umma_commit(tmem_full_bar);
+            for (int k = 0; k < KP / 16; ++k)  // 16 pixels (K) per MMA = 16 rows of 128 B = 2 KB
+              umma_bf16(tmem_u, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc, (it > k_begin || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (it == k_end - 1) umma_commit(tmem_full_bar);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
+        __syncwarp();
       }
     } else if (warp >= 4) {
       const int q = warp & 3;

@@ -20,7 +20,7 @@ extern void spyr_count_launch();
 
 namespace {
 
-constexpr int MAX_GROUPS = 5;
+constexpr int MAX_GROUPS = 3;
 constexpr int HALO_ROWS = 180;                 // (8+2) x (16+2)
 constexpr int HALO_BYTES = 24 * 1024;          // 180 rows x 128 B = 23040, padded to a multiple of 1024
 constexpr int TILE_PIX = 128;                  // 8 x 16 output pixels = reduction length of one stage
@@ -152,15 +152,18 @@ wgrad_halo_kernel(const __grid_constant__ WHMaps maps, const WHParams p) {
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        // ===== MMA issuer (one thread) =====
+      {
+        // ===== MMA issuer: warp-uniform operands, one elected lane issues (see conv_halo.cu) =====
+        const bool issue = elect_one();
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 1, 1);
         const uint64_t base = ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         // B (dy tile): 8-pixel K groups 1024 B apart, 64-column chunks TILE_PIX*128 B apart
         const uint64_t b_hi = base | ((uint64_t)((TILE_PIX * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
         uint64_t a_hi[MAX_GROUPS];
         uint32_t a_row16[MAX_GROUPS];
-        for (int g = 0; g < ngroups; ++g) {
+#pragma unroll
+        for (int g = 0; g < MAX_GROUPS; ++g) {
           a_hi[g] = base | ((uint64_t)((uint32_t)groups[g].lbo >> 4) << 16) | ((uint64_t)(1280 >> 4) << 32);
           a_row16[g] = (uint32_t)groups[g].row0 * 8u;
         }
@@ -173,22 +176,28 @@ wgrad_halo_kernel(const __grid_constant__ WHMaps maps, const WHParams p) {
           tc_fence_after();
           const uint32_t a_lo = smem16 + (uint32_t)stage * stage16;
           const uint64_t db0 = b_hi | (uint64_t)(a_lo + a16);
-          for (int g = 0; g < ngroups; ++g) {
-            const uint64_t da0 = a_hi[g] | (uint64_t)(a_lo + a_row16[g]);
-            const uint32_t acc = tmem_base + (uint32_t)(g * p.bn_cols);
+          if (issue) {
 #pragma unroll
-            for (int k = 0; k < TILE_PIX / 16; ++k)
-              // 16 pixels per MMA: two 8-pixel tile rows -> A advances 2 halo rows of 10 pixels (2560 B), B 2048 B
-              umma_bf16(acc, da0 + (uint64_t)(k * (2560 >> 4)), db0 + (uint64_t)(k * (2048 >> 4)), idesc,
-                        (t > t_begin || k > 0) ? 1u : 0u);
+            for (int g = 0; g < MAX_GROUPS; ++g) {
+              if (g < ngroups) {
+                const uint64_t da0 = a_hi[g] | (uint64_t)(a_lo + a_row16[g]);
+                const uint32_t acc = tmem_u + (uint32_t)(g * p.bn_cols);
+#pragma unroll
+                for (int k = 0; k < TILE_PIX / 16; ++k)
+                  // 16 pixels per MMA: two 8-pixel tile rows -> A advances 2 halo rows of 10 pixels (2560 B), B 2048 B
+                  umma_bf16(acc, da0 + (uint64_t)(k * (2560 >> 4)), db0 + (uint64_t)(k * (2048 >> 4)), idesc,
+                            (t > t_begin || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(done_bar);
+        if (issue) umma_commit(done_bar);
+        __syncwarp();
       }
     } else if (warp >= 4) {
       // ===== epilogue: TMEM -> red.global.add.f32 =====

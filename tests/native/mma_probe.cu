@@ -16,7 +16,7 @@ struct ProbeArgs {
   int a_row0;        // first row of A inside the tile (unaligned starts, halo taps)
   int a_tmem;        // 1: A operand read from tensor memory
   int iters;         // MMAs issued
-  int commit_every;  // tcgen05.commit cadence (0 = only at the end)
+  int uniform_issue; // 1: warp-uniform operands + elected issue (no per-MMA R2UR/waterfall code)
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -55,7 +55,40 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, long long* c
   tc_fence_after();
   const uint32_t tmem = tmem_base_holder;
   long long t0 = 0, t1 = 0;
-  if (threadIdx.x == 0) {
+  if (a.uniform_issue) {
+    // whole warp 0 runs the loop with warp-uniform operands (uniform datapath); only the MMA itself is elected
+    if (threadIdx.x < 32) {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t idesc = umma_idesc_bf16(a.M, a.N, a.a_mn, a.b_mn);
+      const uint32_t a_addr = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + a.a_row0 * 128;
+      const uint32_t b_addr = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + 64 * 1024;
+      const uint64_t da0 = a.a_mn ? umma_smem_desc_sw128(a_addr, 8192, 1024) : umma_smem_desc_sw128(a_addr, 16, a.sbo_a);
+      const uint64_t db0 = a.b_mn ? umma_smem_desc_sw128(b_addr, 8192, 1024) : umma_smem_desc_sw128(b_addr, 16, 1024);
+      const uint32_t a_step = a.a_mn ? (2048 >> 4) : (32 >> 4);
+      const uint32_t b_step = a.b_mn ? (2048 >> 4) : (32 >> 4);
+      const uint32_t a_t = tm + 448;
+      const bool leader = elect_one();
+      t0 = clock64();
+      for (int it = 0; it < a.iters; it += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (leader) {
+            if (a.a_tmem)
+              umma_bf16_ts(tm, a_t + k * 8, db0 + (uint64_t)(k * b_step), idesc, 1);
+            else
+              umma_bf16(tm, da0 + (uint64_t)(k * a_step), db0 + (uint64_t)(k * b_step), idesc, 1);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        t1 = clock64();
+        clocks_out[blockIdx.x] = t1 - t0;
+      }
+      __syncwarp();
+    }
+  } else if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(a.M, a.N, a.a_mn, a.b_mn);
     const uint32_t a_addr = smem_u32(smem) + a.a_row0 * 128;
     const uint32_t b_addr = smem_u32(smem) + 64 * 1024;
@@ -76,9 +109,6 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, long long* c
       else
         umma_bf16(d, da0 + (uint64_t)(k * a_step), db0 + (uint64_t)(k * b_step), idesc, 1);
       if (++acc == a.n_acc) acc = 0;
-      if (a.commit_every && (it % a.commit_every) == a.commit_every - 1 && it + 1 < a.iters) {
-        // a commit nobody waits for would unbalance the barrier: use it as a pure pipeline marker via a second barrier
-      }
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0);
@@ -134,6 +164,17 @@ int main(int argc, char** argv) {
     a.n_acc = 512 / N > 4 ? 4 : (448 / N);
     if (a.n_acc < 1) a.n_acc = 1;
     run(a, ctas, "K-major A,B  round-robin accumulators");
+  }
+  for (int N : {64, 128, 256}) {
+    ProbeArgs a = base;
+    a.N = N;
+    a.uniform_issue = 1;
+    run(a, ctas, "uniform issue, smem A");
+    a.a_tmem = 1;
+    run(a, ctas, "uniform issue, TMEM A");
+    a.a_tmem = 0;
+    a.M = 64;
+    run(a, ctas, "uniform issue, M=64");
   }
   for (int N : {64, 128, 256}) {
     ProbeArgs a = base;

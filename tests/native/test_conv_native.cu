@@ -380,6 +380,10 @@ int main(int argc, char** argv) {
     fails += test_fprop(2, 16, 16, 64, 128, 3, 1, false, 0, 64);  // explicit N tile
     fails += test_fprop(20, 1, 1, 512, 365, 1, 1, false, 4, 128); // linear layer as 1x1, split-K, ragged Cout
     fails += test_fprop(2, 8, 8, 256, 128, 3, 1, false, 3, 0);
+    // more tiles than SMs: resident weights reused across the tiles of a CTA, deep halo ring of the thin 1x1 layers
+    fails += test_fprop(3, 128, 128, 64, 64, 3, 1, false, 0, 0);
+    fails += test_fprop(3, 128, 128, 32, 64, 1, 1, true, 0, 0);
+    fails += test_fprop(3, 128, 128, 64, 64, 3, 2, true, 0, 0);
   }
   if (!strcmp(mode, "all") || !strcmp(mode, "wgrad")) {
     fails += test_wgrad(2, 16, 16, 64, 64, 3, 0, 0, 1);
@@ -406,6 +410,7 @@ int main(int argc, char** argv) {
     fails += test_dgrad(2, 32, 32, 32, 64, 1, true);   // im2col'd first layer: 32 output channels
     fails += test_dgrad(5, 4, 4, 512, 768, 3, true);
     fails += test_dgrad(2, 16, 16, 8, 64, 1, true);    // padded 3-channel skip path
+    fails += test_dgrad(3, 128, 128, 64, 64, 3, true); // resident MN-major weights, several tiles per CTA
     fails += test_per_image(3, 32, 32, 32, 256, 0);    // S = Q K^T
     fails += test_per_image(3, 32, 32, 256, 128, 1);   // O = P V
     fails += test_per_image(3, 32, 32, 128, 256, 0);   // dP = dO V^T
