@@ -197,6 +197,8 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- misc math ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -331,6 +331,19 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           mk_mode[sub] = all0 ? 0 : (all1 ? 1 : 2);
         }
       }
+      if (p.dmask != nullptr || p.residual != nullptr) {
+        // the gate / residual operands of this tile are known before its accumulator is: pull them into L2 while the
+        // MMAs still run, so the epilogue's loads see L2 latency instead of HBM latency
+        for (int sub = 0; sub < p.msub; ++sub) {
+          const size_t pix = ((size_t)n * p.H + (h0 + sub * 16 + (m >> 3))) * p.W + w;
+          for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+            if (n_off + c0 >= p.Cout) break;
+            const size_t off = pix * p.Cout + n_off + c0;
+            if (p.dmask != nullptr) prefetch_l2(p.dmask + off);
+            if (p.residual != nullptr) prefetch_l2(p.residual + off);
+          }
+        }
+      }
       mbar_wait(&acc_full[buf], acc_ph);
       tc_fence_after();
       for (int sub = 0; sub < p.msub; ++sub) {

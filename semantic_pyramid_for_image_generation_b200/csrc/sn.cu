@@ -187,33 +187,29 @@ constexpr int BT = 32;  // backward tile: 32 rows (cout) x BTC input channels x 
 __host__ __device__ inline int sn_btc(int taps) { return taps == 1 ? 9 * BT : BT; }
 
 // pass 1: dots[l] += sum G * W      pass 2: out = (G - dots/sigma * u v^T) / sigma
-template <int PASS>
-__global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, const float* __restrict__ gw_arena,
-                              const float* __restrict__ saved, float* __restrict__ dots, float* __restrict__ grad_arena) {
-  extern __shared__ float gsh[];  // [taps][BT ci][BT+1 co]
-  __shared__ int sh_idx;
-  __shared__ float red[32];
-  const int l = find_layer(tab, n, blockIdx.x, 3, &sh_idx);
-  const spyr_sn_layer L = tab[l];
-  if (L.gw_off < 0) return;
-  const int tile = blockIdx.x - L.tile0_bwd;
-  const int btc = sn_btc(L.taps);
+// TAPS is a compile-time copy of L.taps for the two shapes that carry all the bytes (1 and 9): the index split
+// e -> (ci, t) is then a multiply-shift instead of an integer division per element.
+template <int PASS, int TAPS>
+__device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, const float* __restrict__ gw_arena,
+                                            const float* __restrict__ saved, float* __restrict__ dots,
+                                            float* __restrict__ grad_arena, float* gsh, float* red) {
+  const int taps = TAPS > 0 ? TAPS : L.taps;
+  const int btc = sn_btc(taps);
   const int ctiles = (L.cin + btc - 1) / btc;
   const int co0 = (tile / ctiles) * BT, ci0 = (tile % ctiles) * btc;
   const int nco = min(BT, L.rows - co0), nci = min(btc, L.cin - ci0);
   const float* gw = gw_arena + L.gw_off;
-  const int taps = L.taps;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (L.gw_layout == 1) {
     // coalesced along cout
     for (int r = wid; r < taps * nci; r += nw) {
-      const int t = r / nci, ci = r % nci;
+      const int t = r / nci, ci = r - t * nci;
       if (lane < nco) gsh[(t * btc + ci) * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
     }
   } else {
     for (int r = wid; r < nco; r += nw)
       for (int e = lane; e < nci * taps; e += 32) {
-        const int ci = e / taps, t = e % taps;
+        const int ci = e / taps, t = e - ci * taps;
         gsh[(t * btc + ci) * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
       }
   }
@@ -225,8 +221,8 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
     for (int r = wid; r < nco; r += nw) {
       const float* wrow = L.w + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
-        const int ci = e / taps, t = e % taps;
-        acc += gsh[(t * btc + ci) * (BT + 1) + r] * wrow[e];
+        const int ci = e / taps, t = e - ci * taps;
+        acc += gsh[(t * btc + ci) * (BT + 1) + r] * __ldg(wrow + e);
       }
     }
     acc = block_sum(acc, red);
@@ -235,16 +231,34 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
     const float inv = 1.f / sigma;
     const float coef = dots[L.index] * inv;  // <G, W/sigma>
     float* out = grad_arena + L.grad_off;
+    const float* vv = sv + 1 + L.rows + (size_t)ci0 * taps;
     for (int r = wid; r < nco; r += nw) {
       const float ur = sv[1 + co0 + r] * coef;
       float* orow = out + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
-      const float* vv = sv + 1 + L.rows + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
-        const int ci = e / taps, t = e % taps;
-        orow[e] = (gsh[(t * btc + ci) * (BT + 1) + r] - ur * vv[e]) * inv;
+        const int ci = e / taps, t = e - ci * taps;
+        orow[e] = (gsh[(t * btc + ci) * (BT + 1) + r] - ur * __ldg(vv + e)) * inv;
       }
     }
   }
+}
+
+template <int PASS>
+__global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, const float* __restrict__ gw_arena,
+                              const float* __restrict__ saved, float* __restrict__ dots, float* __restrict__ grad_arena) {
+  extern __shared__ float gsh[];  // [taps][BT ci][BT+1 co]
+  __shared__ int sh_idx;
+  __shared__ float red[32];
+  const int l = find_layer(tab, n, blockIdx.x, 3, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  if (L.gw_off < 0) return;
+  const int tile = blockIdx.x - L.tile0_bwd;
+  if (L.taps == 9)
+    sn_bwd_tile<PASS, 9>(L, tile, gw_arena, saved, dots, grad_arena, gsh, red);
+  else if (L.taps == 1)
+    sn_bwd_tile<PASS, 1>(L, tile, gw_arena, saved, dots, grad_arena, gsh, red);
+  else
+    sn_bwd_tile<PASS, 0>(L, tile, gw_arena, saved, dots, grad_arena, gsh, red);
 }
 
 }  // namespace

@@ -179,6 +179,20 @@ int main(int argc, char** argv) {
   for (int N : {64, 128, 256}) {
     ProbeArgs a = base;
     a.N = N;
+    a.uniform_issue = 1;
+    a.sbo_a = 1280;
+    a.a_row0 = 11;
+    run(a, ctas, "uniform issue, halo A (SBO 1280, row0 11)");
+    a.b_mn = 1;
+    run(a, ctas, "uniform issue, halo A + B MN-major (dgrad)");
+    a.sbo_a = 1024;
+    a.a_row0 = 0;
+    a.a_mn = 1;
+    run(a, ctas, "uniform issue, A,B MN-major (wgrad)");
+  }
+  for (int N : {64, 128, 256}) {
+    ProbeArgs a = base;
+    a.N = N;
     a.sbo_a = 1280;
     a.a_row0 = 11;
     run(a, ctas, "halo A (SBO 1280, row0 11)");
