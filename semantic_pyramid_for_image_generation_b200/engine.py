@@ -196,7 +196,7 @@ def _gblock_backward(blk, key, st, sn, ga, gw, grad, ctx, cls, g_out):
     ops.wgrad(a2, g_out, sn.gw_ptr(gw, k6), B, H2, W2, Cout, Cout, 3)
     ops.wgrad(xu, g_out, sn.gw_ptr(gw, kr), B, H2, W2, Cin, Cout, 1)
     ops.wgrad(fm, g_out, sn.gw_ptr(gw, kf), B, H2, W2, Cf, Cout, 3, cin_stride=Cf + 1)
-    call("spyr_stencil_wgrad", mask.data_ptr(), g_out.data_ptr(), B, H2, W2, Cout, sn.gw_ptr(gw, kf), Cf + 1, Cf)
+    ops.stencil_wgrad(mask, g_out, B, H2, W2, Cout, sn.gw_ptr(gw, kf), Cf + 1, Cf)
     gy2, _ = ops.conv(B, H2, W2, Cout, [Src(g_out, st.w(k6), Cout, 3, mn=True)], dmask=a2, dmask_slope=LRELU)
     g_h1 = _cbn_backward(blk.main_block[4], ga, grad, h1, mr2, cls, gy2, 0)
     ops.wgrad(a, g_h1, sn.gw_ptr(gw, k3), B, H2, W2, Cin, Cout, 3)
@@ -273,6 +273,7 @@ def generator_backward(G, ctx, g_img):
     grad = ga.new(dev)
     gw = torch.zeros(sn.gw_floats, dtype=F32, device=dev)
     g_img = _f32c(g_img)
+    ops.LEAF.begin(dev)  # weight/bias-gradient kernels from here on overlap the input-gradient chain
     x, mr, a, a3, img = ctx["xf"], ctx["mr"], ctx["a"], ctx["a3"], ctx["img"]
     B, H, W, c5 = x.shape
     f3, f5_ = G.final_block[3], G.final_block[5]
@@ -327,6 +328,7 @@ def generator_backward(G, ctx, g_img):
                      xmask=ctx["m6"])
     g_h0 = ops.linear_bwd_x(g_h1, m1.weight_orig, st.sigma("linear_block_1.main_block.1"), x=h0, in_slope=LRELU)
     ops.linear_bwd_w(g_h0, ctx["z"], sn.gw_ptr(gw, "linear_layer"), ga.ptr(grad, G.linear_layer.bias))
+    ops.LEAF.join()
     sn.backward(st, gw, grad)
     return grad
 
@@ -422,6 +424,8 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
     g_out = _f32c(g_out)
     grad = ga.new(dev)
     gw = torch.zeros(sn.gw_floats, dtype=F32, device=dev)
+    if want_wgrad:
+        ops.LEAF.begin(dev)
     feat0, feat, x7 = ctx["feat0"], ctx["feat"], ctx["x7"]
     E = feat.shape[1]
     l11 = D.layers[11]
@@ -471,6 +475,7 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
         g8, _ = ops.conv(B, H // 2, W // 2, 8, [Src(g, st.w("layers.0.residual_mapping"), C0, 1, mn=True)])
         call("spyr_img_avgpool_pad8_bwd", g8.data_ptr(), B, H, W, g_img.data_ptr(), 1)
     if want_wgrad:
+        ops.LEAF.join()
         sn.backward(st, gw, grad)
         return grad, g_img
     return None, g_img

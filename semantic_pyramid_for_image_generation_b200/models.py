@@ -217,13 +217,18 @@ class _DiscriminatorFn(torch.autograd.Function):
         if grad is not None:
             ga, prev = module._ga, module._last_grad_arena
             p0 = ga.params[0]
-            if all(needs) and prev is not None and p0.grad is not None and prev.device == grad.device and \
-                    p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]:
-                # second backward pass of an accumulation window (D(real) + D(fake), model_wrapper.py:153-160): every
-                # .grad is a view of the previous arena, so one flat add replaces 56 per-parameter accumulations
+            task = torch._C._current_graph_task_id()
+            same_pass = prev is not None and task >= 0 and getattr(module, "_grad_task", -1) == task
+            earlier_pass = prev is not None and p0.grad is not None and \
+                p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]
+            if all(needs) and prev is not None and prev.device == grad.device and (same_pass or earlier_pass):
+                # D(real) and D(fake) (model_wrapper.py:153-160) both feed every parameter.  The views of the first
+                # arena are either still waiting in autograd's input buffers (same backward pass) or already are the
+                # .grad tensors (an earlier pass): one flat add into that arena replaces 56 per-parameter additions.
                 call("spyr_add_inplace", prev.data_ptr(), grad.data_ptr(), grad.numel())
             else:
                 module._last_grad_arena = grad
+                module._grad_task = task
                 pg = module._ga.views(grad, needs)
         return (None, g_img, None) + tuple(pg)
 

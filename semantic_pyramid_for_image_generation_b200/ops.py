@@ -4,6 +4,7 @@ Feature maps are torch tensors of shape (B, H, W, C), dtype bfloat16, contiguous
 losses and master weights are float32.  Nothing here computes on the host or through torch kernels.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -28,6 +29,55 @@ def _profiled(kernel, flops, nbytes, name, desc, label=""):
     call(name, desc)
     e1.record()
     PROFILE.append((kernel, flops, nbytes, e0, e1, label))
+
+
+class LeafStream(object):
+    """Second CUDA stream for the leaves of a backward pass.
+
+    Weight/bias-gradient kernels (conv wgrad, colsum, stencil wgrad, linear wgrad) consume a gradient map and a saved
+    activation and produce a slice of the gradient arenas that nothing reads before the spectral-norm backward at the
+    end of the pass.  Run after `begin()`, they are enqueued on a side stream that waits for the main stream's current
+    point, so the small-map launches (a few dozen CTAs) overlap the input-gradient chain instead of each taking a turn
+    on a mostly idle GPU.  `join()` makes the main stream wait for them.  Inputs are kept alive until `join()` (the
+    caching allocator would otherwise hand a freed gradient map to the next main-stream allocation).  Works the same
+    under CUDA-graph capture, where the waits become graph edges.  SPYR_LEAF_STREAM=0 disables it."""
+
+    def __init__(self):
+        self.enabled = os.environ.get("SPYR_LEAF_STREAM", "1") != "0"
+        self.streams = {}
+        self.active = None
+        self.keep = []
+
+    def begin(self, device):
+        if self.active is not None:  # a pass that raised before its join(): close it
+            self.join()
+        if not self.enabled or PROFILE is not None:
+            return False
+        key = (device.type, device.index)
+        if key not in self.streams:
+            self.streams[key] = torch.cuda.Stream(device=device)
+        self.active = self.streams[key]
+        return True
+
+    def run(self, tensors, name, *args):
+        if self.active is None:
+            call(name, *args)
+            return
+        side = self.active
+        side.wait_stream(torch.cuda.current_stream())
+        self.keep.extend(tensors)
+        with torch.cuda.stream(side):
+            call(name, *args)
+
+    def join(self):
+        if self.active is None:
+            return
+        torch.cuda.current_stream().wait_stream(self.active)
+        self.active = None
+        del self.keep[:]
+
+
+LEAF = LeafStream()
 
 
 def empty_bf16(*shape, device=None):
@@ -125,7 +175,10 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
     d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw_ptr
     d.cin_stride, d.per_image = cin_stride, int(per_image)
     if PROFILE is None:
-        call("spyr_conv2d_wgrad", C.byref(d))
+        if per_image:
+            call("spyr_conv2d_wgrad", C.byref(d))  # attention dK / dV feed the rest of the backward: not a leaf
+        else:
+            LEAF.run((x, dy), "spyr_conv2d_wgrad", C.byref(d))
     else:
         npx = B * H * W
         _profiled("conv_wgrad_kernel", 2.0 * npx * Cin * Cout * ksize * ksize,
@@ -135,7 +188,12 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
 
 def colsum(g, C_, out0, out1=None, out2=None):
     rows = g.numel() // C_
-    call("spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2)
+    LEAF.run((g,), "spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2)
+
+
+def stencil_wgrad(mask, dy, B, H, W, Cout, gw_ptr, cin_stride, cin_index):
+    """Weight gradient of the mask channel of cat(feature*mask, mask) (models.py:94): nine masked sums of dy."""
+    LEAF.run((mask, dy), "spyr_stencil_wgrad", mask.data_ptr(), dy.data_ptr(), B, H, W, Cout, gw_ptr, cin_stride, cin_index)
 
 
 def maskgate(f, mask):
@@ -246,7 +304,8 @@ def linear_bwd_x(gy, w, sigma_ptr, y=None, out_slope=1.0, x=None, in_slope=1.0, 
 def linear_bwd_w(gy, x, gw_ptr, gb_ptr, y=None, out_slope=1.0, xmask=None, in_slope=1.0):
     B, O = gy.shape
     K = x.shape[1]
-    call("spyr_linear_bwd_w", gy.data_ptr(), ptr(y), out_slope, x.data_ptr(), ptr(xmask), in_slope, gw_ptr, gb_ptr, B, K, O)
+    LEAF.run((gy, x, y, xmask), "spyr_linear_bwd_w", gy.data_ptr(), ptr(y), out_slope, x.data_ptr(), ptr(xmask), in_slope,
+             gw_ptr, gb_ptr, B, K, O)
 
 
 def argmax_rows(onehot):
