@@ -78,18 +78,35 @@ class ModelWrapper(object):
     # ------------------------------------------------------------------------------------------------
     # one iteration of model_wrapper.py:136-190
     # ------------------------------------------------------------------------------------------------
+    def _second_stream(self, device):
+        """Side stream for the network-level overlap inside a phase (None when SPYR_PHASE_STREAMS=0)."""
+        if os.environ.get("SPYR_PHASE_STREAMS", "1") == "0":
+            return None
+        key = (device.type, device.index)
+        streams = self.__dict__.setdefault("_phase_streams", {})
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
+
     def _phase_discriminator(self, images_real, labels, masks, z_d):
         """VGG(real), G (no grad), D(real), D(fake), LSGAN loss, backward.  Leaves D's gradients in D's flat arena."""
         G, D, V = self.generator, self.discriminator, self.vgg16
         batch, device = images_real.shape[0], images_real.device
         G.zero_grad(set_to_none=True)
         D.zero_grad(set_to_none=True)
-        with torch.no_grad():
+        # VGG(real) -> G (both without autograd) run on a second stream while D(real) runs on this one: the small maps at
+        # the start of G and at the end of D leave most SMs idle, the 256x256 layers of the other network fill them
+        main, side = torch.cuda.current_stream(), self._second_stream(device)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
             features_real = V(images_real)
             if z_d is None:
                 z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
             images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
         prediction_real = D(images_real, labels)
+        if side is not None:
+            main.wait_stream(side)
         prediction_fake = D(images_fake, labels)
         loss_d_real, loss_d_fake = self.discriminator_loss(prediction_real, prediction_fake)
         (loss_d_real + loss_d_fake).backward()
@@ -108,10 +125,18 @@ class ModelWrapper(object):
             if z_g is None:
                 z_g = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
             images_fake = G(input=z_g, features=features_real, masks=masks, class_id=labels.float())
+            # VGG(fake) on the second stream next to D(fake); autograd runs each backward on its forward's stream, so the
+            # two input-gradient chains overlap as well and meet at images_fake
+            main, side = torch.cuda.current_stream(), self._second_stream(device)
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                features_fake = V(images_fake)
             prediction_fake = D(images_fake, labels)
             loss_g = self.generator_loss(prediction_fake)
             loss_div = w_div * self.diversity_loss(images_fake, z_g)
-            features_fake = V(images_fake)
+            if side is not None:
+                main.wait_stream(side)
             loss_rec = w_rec * self.semantic_reconstruction_loss(features_real, features_fake, masks)
             (loss_g + loss_rec + loss_div).backward()
         finally:
