@@ -117,7 +117,13 @@ class ModelWrapper(object):
         weight gradients are not requested (the reference computes and discards them)."""
         G, D, V = self.generator, self.discriminator, self.vgg16
         batch, device = labels.shape[0], labels.device
-        self.discriminator_optimizer.step()
+        # D's Adam step (HBM-bound, reads D's gradient arena) only has to finish before D is used again: it shares the GPU
+        # with the generator forward, whose first layers are 4x4 ... 32x32 maps
+        main, side = torch.cuda.current_stream(), self._second_stream(device)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            self.discriminator_optimizer.step()
         G.zero_grad(set_to_none=True)
         D.zero_grad(set_to_none=True)
         _set_requires_grad(D, False)
@@ -127,8 +133,8 @@ class ModelWrapper(object):
             images_fake = G(input=z_g, features=features_real, masks=masks, class_id=labels.float())
             # VGG(fake) on the second stream next to D(fake); autograd runs each backward on its forward's stream, so the
             # two input-gradient chains overlap as well and meet at images_fake
-            main, side = torch.cuda.current_stream(), self._second_stream(device)
             if side is not None:
+                main.wait_stream(side)  # D's new weights
                 side.wait_stream(main)
             with torch.cuda.stream(side if side is not None else main):
                 features_fake = V(images_fake)
