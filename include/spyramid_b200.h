@@ -117,6 +117,18 @@ int spyr_nchw_to_nhwc(const float* src, const float* mask, float slope, void* ds
 int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slope, float* dst, int B, int C, int HW, void* stream);
 int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream);
 
+/* ---- input pipeline: what the reference's DataLoader workers compute per sample, on the device ----
+ * One pyramid level of the mask set of B samples from their descriptors (misc.py:47-67).  `depth` counts levels from the
+ * deepest (0 = logits (365), 1 = fc7 (4096), 2 = 8x8 ... 6 = 128x128); vector levels use H = 1.  stage[b] is the kept
+ * level; bitmap_hw[b] > 0 marks a spatial sample whose square uint8 {0,1} bitmap (row-major, bitmap_hw x bitmap_hw,
+ * at bitmaps + b * bitmap_stride) shows through every level shallower than stage[b], nearest-neighbour resized.
+ * out: f32 [B, H*W], values exactly 0.0 / 1.0. */
+int spyr_expand_mask_level(const int* stage, const int* bitmap_hw, const unsigned char* bitmaps, long long bitmap_stride,
+                           int B, int depth, int H, int W, float* out, void* stream);
+/* data.py:49-53: uint8 planes (B*C of them, `plane` bytes each) -> x/255 -> per-plane min-max to [-1, 1]
+ * (kornia.normalize_min_max, eps 1e-6), FP32 out, same rounding as the reference's expression */
+int spyr_image_u8_minmax_normalize(const unsigned char* img, int planes, long long plane, float* out, void* stream);
+
 /* pooling (NHWC bf16; H, W are the HIGH-resolution dims everywhere) */
 int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_raw, void* y_act, float slope, int B, int H, int W, int C,
                       void* stream); /* models.py:406,415-418,451,465; residual is added after pooling */

@@ -195,6 +195,9 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
                                             float* __restrict__ grad_arena, float* gsh, float* red) {
   const int taps = TAPS > 0 ? TAPS : L.taps;
   const int btc = sn_btc(taps);
+  // tap stride == 4 (mod 32 banks): the 32 lanes of a row sweep (ci, t) pairs, and with a stride == 0 the nine taps
+  // of one ci would share a bank
+  const int tstride = btc * (BT + 1) + 4;
   const int ctiles = (L.cin + btc - 1) / btc;
   const int co0 = (tile / ctiles) * BT, ci0 = (tile % ctiles) * btc;
   const int nco = min(BT, L.rows - co0), nci = min(btc, L.cin - ci0);
@@ -204,13 +207,13 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
     // coalesced along cout
     for (int r = wid; r < taps * nci; r += nw) {
       const int t = r / nci, ci = r - t * nci;
-      if (lane < nco) gsh[(t * btc + ci) * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
+      if (lane < nco) gsh[t * tstride + ci * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
     }
   } else {
     for (int r = wid; r < nco; r += nw)
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e - ci * taps;
-        gsh[(t * btc + ci) * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
+        gsh[t * tstride + ci * (BT + 1) + r] = gw[(size_t)(co0 + r) * L.cols + (size_t)(ci0 + ci) * taps + t];
       }
   }
   __syncthreads();
@@ -222,7 +225,7 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
       const float* wrow = L.w + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e - ci * taps;
-        acc += gsh[(t * btc + ci) * (BT + 1) + r] * __ldg(wrow + e);
+        acc += gsh[t * tstride + ci * (BT + 1) + r] * __ldg(wrow + e);
       }
     }
     acc = block_sum(acc, red);
@@ -237,7 +240,7 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
       float* orow = out + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e - ci * taps;
-        orow[e] = (gsh[(t * btc + ci) * (BT + 1) + r] - ur * __ldg(vv + e)) * inv;
+        orow[e] = (gsh[t * tstride + ci * (BT + 1) + r] - ur * __ldg(vv + e)) * inv;
       }
     }
   }
@@ -318,7 +321,7 @@ extern "C" int spyr_sn_backward(const spyr_sn_layer* dev_tab, int n, const spyr_
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(dev_tab && plan && gw_arena && saved && dots && grad_arena, "sn_backward: bad arguments");
   SPYR_CHECK_CUDA(cudaMemsetAsync(dots, 0, sizeof(float) * n, stream));
-  const size_t smem = (size_t)9 * BT * (BT + 1) * sizeof(float);
+  const size_t smem = (size_t)9 * (BT * (BT + 1) + 4) * sizeof(float);
   sn_bwd_kernel<1><<<plan->tiles_bwd, 256, smem, stream>>>(dev_tab, n, gw_arena, saved, dots, grad_arena);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();

@@ -268,3 +268,28 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"]
+
+
+def test_packed_mask_descriptors_round_trip():
+    """Host half of the device input pipeline: descriptors -> flat tensors -> (host re-expansion) == direct expansion."""
+    import random
+    import numpy as np
+    from semantic_pyramid_for_image_generation_b200 import input_pipeline as ip, misc
+    random.seed(5)
+    np.random.seed(5)
+    descs = [misc.draw_mask_descriptor(p_random_mask=0.7) for _ in range(24)]
+    packed = ip.PackedDescriptors(len(descs), pin=False).fill(descs)
+    assert packed.stage.dtype == torch.int32 and packed.bitmaps.dtype == torch.uint8
+    for b, d in enumerate(descs):
+        n = int(packed.bitmap_hw[b])
+        assert int(packed.stage[b]) == d.stage
+        if d.bitmap is None:
+            assert n == 0
+            rebuilt = misc.MaskDescriptor(d.stage, None)
+        else:
+            assert n == d.bitmap.shape[0] and 0 < d.stage < 6
+            rebuilt = misc.MaskDescriptor(d.stage, packed.bitmaps[b, :n * n].view(n, n).numpy())
+        for got, want in zip(misc.expand_mask_descriptor(rebuilt), misc.expand_mask_descriptor(d)):
+            assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        ip.PackedDescriptors(2, pin=False).fill(descs[:3])
