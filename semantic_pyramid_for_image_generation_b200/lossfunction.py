@@ -162,6 +162,11 @@ class LSGANGeneratorLoss(nn.Module):
         return _LsganFn.apply(images_fake, 1.0)
 
 
+def lsgan_term(prediction: torch.Tensor, target: float) -> torch.Tensor:
+    """One least-squares term 0.5 * mean((prediction - target)^2) (reference lossfunction.py:131-137,156-164)."""
+    return _LsganFn.apply(prediction, float(target))
+
+
 class LSGANDiscriminatorLoss(nn.Module):
     '''
     Least squares discriminator loss (reference lossfunction.py:140-164): (0.5 * mean((D(x) - 1)^2), 0.5 * mean(D(G(z))^2))

@@ -18,7 +18,8 @@ import torch
 import torch.nn as nn
 
 from . import misc
-from .lossfunction import (DiversityLoss, LSGANDiscriminatorLoss, LSGANGeneratorLoss, SemanticReconstructionLoss)
+from .lossfunction import (DiversityLoss, LSGANDiscriminatorLoss, LSGANGeneratorLoss, SemanticReconstructionLoss,
+                           lsgan_term)
 from .models import VGG16
 
 METRICS = ("loss_discriminator_real", "loss_discriminator_fake", "loss_generator",
@@ -78,11 +79,11 @@ class ModelWrapper(object):
     # ------------------------------------------------------------------------------------------------
     # one iteration of model_wrapper.py:136-190
     # ------------------------------------------------------------------------------------------------
-    def _second_stream(self, device):
-        """Side stream for the network-level overlap inside a phase (None when SPYR_PHASE_STREAMS=0)."""
+    def _second_stream(self, device, index=0):
+        """Side streams for the network-level overlap inside a phase (None when SPYR_PHASE_STREAMS=0)."""
         if os.environ.get("SPYR_PHASE_STREAMS", "1") == "0":
             return None
-        key = (device.type, device.index)
+        key = (device.type, device.index, index)
         streams = self.__dict__.setdefault("_phase_streams", {})
         if key not in streams:
             streams[key] = torch.cuda.Stream(device=device)
@@ -94,9 +95,12 @@ class ModelWrapper(object):
         batch, device = images_real.shape[0], images_real.device
         G.zero_grad(set_to_none=True)
         D.zero_grad(set_to_none=True)
-        # VGG(real) -> G (both without autograd) run on a second stream while D(real) runs on this one: the small maps at
-        # the start of G and at the end of D leave most SMs idle, the 256x256 layers of the other network fill them
-        main, side = torch.cuda.current_stream(), self._second_stream(device)
+        # Three streams.  `side`: VGG(real) -> G, both without autograd.  `third`: D(real) forward, its LSGAN term and
+        # its whole backward.  This stream: D(fake) forward / loss / backward once the fake images exist.  The small maps
+        # at the start of G and at both ends of D's backward leave most SMs idle; the 256x256 layers of the other
+        # networks fill them.  D(fake)'s spectral-norm iteration must follow D(real)'s (model_wrapper.py:150-153 calls
+        # them in that order on the same u, v): this stream waits for the end of D(real)'s forward.
+        main, side, third = torch.cuda.current_stream(), self._second_stream(device), self._second_stream(device, 1)
         if side is not None:
             side.wait_stream(main)
         with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
@@ -104,12 +108,28 @@ class ModelWrapper(object):
             if z_d is None:
                 z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
             images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
-        prediction_real = D(images_real, labels)
-        if side is not None:
-            main.wait_stream(side)
+        if side is None or not isinstance(self.discriminator_loss, LSGANDiscriminatorLoss):
+            # a user-supplied loss couples the two predictions: D(real) still overlaps VGG -> G, one joint backward
+            prediction_real = D(images_real, labels)
+            if side is not None:
+                main.wait_stream(side)
+            prediction_fake = D(images_fake, labels)
+            loss_d_real, loss_d_fake = self.discriminator_loss(prediction_real, prediction_fake)
+            (loss_d_real + loss_d_fake).backward()
+            return features_real, loss_d_real.detach(), loss_d_fake.detach()
+        third.wait_stream(main)
+        with torch.cuda.stream(third):
+            prediction_real = D(images_real, labels)
+            real_forward_done = torch.cuda.Event()
+            real_forward_done.record(third)
+            loss_d_real = lsgan_term(prediction_real, 1.0)  # the two LSGAN terms are independent (lossfunction.py:156-164)
+            loss_d_real.backward()
+        main.wait_stream(side)
+        main.wait_event(real_forward_done)
         prediction_fake = D(images_fake, labels)
-        loss_d_real, loss_d_fake = self.discriminator_loss(prediction_real, prediction_fake)
-        (loss_d_real + loss_d_fake).backward()
+        loss_d_fake = lsgan_term(prediction_fake, 0.0)
+        loss_d_fake.backward()  # adds into the arena of the first pass once `third` has finished (models._DiscriminatorFn)
+        main.wait_stream(third)
         return features_real, loss_d_real.detach(), loss_d_fake.detach()
 
     def _phase_generator(self, features_real, labels, masks, z_g, w_rec, w_div):

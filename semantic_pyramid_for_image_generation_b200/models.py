@@ -221,14 +221,23 @@ class _DiscriminatorFn(torch.autograd.Function):
             same_pass = prev is not None and task >= 0 and getattr(module, "_grad_task", -1) == task
             earlier_pass = prev is not None and p0.grad is not None and \
                 p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]
+            cur = torch.cuda.current_stream(grad.device)
             if all(needs) and prev is not None and prev.device == grad.device and (same_pass or earlier_pass):
                 # D(real) and D(fake) (model_wrapper.py:153-160) both feed every parameter.  The views of the first
                 # arena are either still waiting in autograd's input buffers (same backward pass) or already are the
                 # .grad tensors (an earlier pass): one flat add into that arena replaces 56 per-parameter additions.
+                # The first pass may have run on another stream: order the add after it, and that stream's later work
+                # (optimizer, all-reduce) after the add.
+                owner = getattr(module, "_grad_stream", None)
+                if owner is not None and owner != cur:
+                    cur.wait_stream(owner)
                 call("spyr_add_inplace", prev.data_ptr(), grad.data_ptr(), grad.numel())
+                if owner is not None and owner != cur:
+                    owner.wait_stream(cur)
             else:
                 module._last_grad_arena = grad
                 module._grad_task = task
+                module._grad_stream = cur
                 pg = module._ga.views(grad, needs)
         return (None, g_img, None) + tuple(pg)
 

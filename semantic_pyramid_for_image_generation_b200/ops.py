@@ -53,7 +53,9 @@ class LeafStream(object):
             self.join()
         if not self.enabled or PROFILE is not None:
             return False
-        key = (device.type, device.index)
+        # one side stream per parent stream: backward passes that run concurrently on different streams (D(real) next to
+        # D(fake), model_wrapper._phase_discriminator) must not queue their leaves behind each other
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
         if key not in self.streams:
             self.streams[key] = torch.cuda.Stream(device=device)
         self.active = self.streams[key]
