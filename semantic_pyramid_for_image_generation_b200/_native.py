@@ -84,6 +84,7 @@ _SIGNATURES = {
     "spyr_conv1x1_tanh_fwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_conv1x1_tanh_bwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_bn_stats": [P, c_int, c_int, c_int, c_int, c_int, P, P],
+    "spyr_up2_stats": [P, c_int, c_int, c_int, c_int, P, P, P],
     "spyr_bn_finalize": [P, c_double, c_int, c_float, c_float, P, P, P, P, c_int, P],
     "spyr_bn_act": [P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],

@@ -28,6 +28,9 @@ void spyr_set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 #define SPYR_LAUNCH_CHECK() SPYR_CHECK_CUDA(cudaGetLastError())
+// kernels that split a flat element index with 32-bit arithmetic (64-bit integer division costs ~100 instructions)
+#define SPYR_N32(n) \
+  SPYR_REQUIRE((long long)(n) < 2147483647LL, "%s: %lld elements exceed the 32-bit index range", __func__, (long long)(n))
 
 typedef __nv_bfloat16 bf16;
 

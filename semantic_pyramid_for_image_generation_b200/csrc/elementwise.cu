@@ -196,8 +196,8 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __re
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % OW);
   t /= OW;
   const int h = (int)(t % OH);
@@ -231,8 +231,8 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __re
 __global__ void avgpool2_bwd_kernel(const bf16* __restrict__ g_lo, bf16* __restrict__ g_hi, int B, int H, int W, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % W);
   t /= W;
   const int h = (int)(t % H);
@@ -248,8 +248,8 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % OW);
   t /= OW;
   const int h = (int)(t % OH);
@@ -276,8 +276,8 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % OW);
   t /= OW;
   const int h = (int)(t % OH);
@@ -329,8 +329,8 @@ __global__ void adaptive_avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __
                                             int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int ow = (int)(t % OW);
   t /= OW;
   const int oh = (int)(t % OH);
@@ -354,8 +354,8 @@ __global__ void adaptive_avgpool_bwd_kernel(const bf16* __restrict__ gy, const b
                                             bf16* __restrict__ gx, int B, int H, int W, int OH, int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % W);
   t /= W;
   const int h = (int)(t % H);
@@ -497,6 +497,7 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16*
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  float acc_all[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const long long npix = (long long)B * H * W;
   if (pr < prows)
     for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
@@ -504,21 +505,32 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16*
       const int h = (int)((p / W) % H);
       const long long bbase = p - (long long)h * W - w;
       float mk[9];
-      bool any = false;
+      bool any = false, all = true;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
         mk[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(mask + bbase + (long long)hh * W + ww) : 0.f;
         any = any || (mk[t] != 0.f);
+        all = all && (mk[t] == 1.f);
       }
       if (!any) continue;
       float a[8];
       ld8(g + (p * cg + c) * 8, a);
+      if (all) {
+        // interior of a kept region (masks are 0/1 and mostly constant per sample): one sum serves all nine taps
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_all[j] += a[j];
+        continue;
+      }
 #pragma unroll
       for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[t][j] += mk[t] * a[j];
     }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] += acc_all[j];
   if (pr < prows) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
@@ -566,7 +578,7 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H
                                      int act, float act_slope) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
-  const int c = (int)(idx % cg);
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
   const long long pix = idx / cg;
   const int C = cg * 8;
   float v[8];
@@ -788,6 +800,7 @@ extern "C" int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_ra
   SPYR_C8(C);
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  SPYR_N32(n);
   avgpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)residual,
                                                                           (bf16*)y_raw, (bf16*)y_act, slope, B, H, W, C / 8);
   spyr_count_launch();
@@ -797,6 +810,7 @@ extern "C" int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_ra
 extern "C" int spyr_avgpool2_bwd(const void* g_lo, void* g_hi, int B, int H, int W, int C, void* stream) {
   SPYR_C8(C);
   const long long n = (long long)B * H * W * (C / 8);
+  SPYR_N32(n);
   avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g_lo, (bf16*)g_hi, B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -806,6 +820,7 @@ extern "C" int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, in
   SPYR_C8(C);
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  SPYR_N32(n);
   maxpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -815,6 +830,7 @@ extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B,
                                  int accumulate, void* stream) {
   SPYR_C8(C);
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  SPYR_N32(n);
   maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gy, (bf16*)gx, B, H,
                                                                           W, C / 8, relu_gate, accumulate);
   spyr_count_launch();
@@ -824,6 +840,7 @@ extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B,
 extern "C" int spyr_adaptive_avgpool_fwd(const void* x, void* y, int B, int H, int W, int OH, int OW, int C, void* stream) {
   SPYR_C8(C);
   const long long n = (long long)B * OH * OW * (C / 8);
+  SPYR_N32(n);
   adaptive_avgpool_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, OH, OW,
                                                                                   C / 8);
   spyr_count_launch();
@@ -834,6 +851,7 @@ extern "C" int spyr_adaptive_avgpool_bwd(const void* gy, const void* residual, v
                                          int OW, int C, void* stream) {
   SPYR_C8(C);
   const long long n = (long long)B * H * W * (C / 8);
+  SPYR_N32(n);
   adaptive_avgpool_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)gy, (const bf16*)residual, (bf16*)gx, B, H, W, OH, OW, C / 8);
   spyr_count_launch();

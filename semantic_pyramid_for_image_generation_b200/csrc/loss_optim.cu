@@ -107,8 +107,8 @@ __global__ void rec_level_fwd_kernel(const bf16* __restrict__ fr, const bf16* __
   const long long n = (long long)B * OH * OW * cg;
   float acc = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % cg);
-    long long t = idx / cg;
+    const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+    int t = (int)((unsigned)idx / (unsigned)cg);
     const int w = (int)(t % OW);
     t /= OW;
     const int h = (int)(t % OH);
@@ -138,8 +138,8 @@ __global__ void rec_level_bwd_kernel(const bf16* __restrict__ fr, const bf16* __
   const size_t C = (size_t)cg * 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
-  const int c = (int)(idx % cg);
-  long long t = idx / cg;
+  const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+  int t = (int)((unsigned)idx / (unsigned)cg);
   const int w = (int)(t % OW);
   t /= OW;
   const int h = (int)(t % OH);
@@ -322,6 +322,7 @@ extern "C" int spyr_rec_level_fwd(const void* fr, const void* ff, const float* m
                                   void* stream) {
   SPYR_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "rec_level_fwd: bad shape");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  SPYR_N32(n);
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
   long long want = (n + 1023) / 1024;
   const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
@@ -335,6 +336,7 @@ extern "C" int spyr_rec_level_bwd(const void* fr, const void* ff, const float* m
                                   const float* gout, void* gff, void* stream) {
   SPYR_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "rec_level_bwd: bad shape");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  SPYR_N32(n);
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
   rec_level_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)fr, (const bf16*)ff, mask, B,
                                                                                  H, W, C / 8, inv, gout, (bf16*)gff);

@@ -111,7 +111,11 @@ __device__ __forceinline__ void up2_load(const bf16* x, int b, int oh, int ow, i
 // ---------------------------------------------------------------------------------------------
 // statistics
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W, int cg, int up2, double* __restrict__ sums) {
+// The kernels below are templated on their mode: one body per mode keeps the plain same-resolution cases at ~40
+// registers (full occupancy) instead of inheriting the register count of the interpolating variants.
+template <int up2>
+__global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W, int cg, bf16* __restrict__ xu_out,
+                                double* __restrict__ sums) {
   extern __shared__ float sh[];  // [prows][2][C]
   const int C = cg * 8;
   const int c = threadIdx.x % cg;
@@ -132,6 +136,12 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
         divmod((int)p, OW, sh_w, rowi, ow);
         divmod(rowi, OH, sh_h, b, oh);
         up2_load(x, b, oh, ow, H, W, cg, c, shs, sws, v);
+        if (xu_out != nullptr) {
+          // materialise up2(x) once; the statistics are those of the stored (BF16) values the later passes read
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
+          st8(xu_out + (p * cg + c) * 8, v);
+        }
       } else {
         ld8(x + (p * cg + c) * 8, v);
       }
@@ -189,9 +199,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // Channel-group-stationary: a thread keeps the affine parameters of its 8 channels (of ONE sample: blockIdx.y) in
 // registers and walks over output pixels, so the per-element work is one 16-byte load (four for the bilinear modes)
 // and one or two 16-byte stores.
+template <int mode>
 __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ mean_rstd,
                               const float* __restrict__ scale_ptr, const float* __restrict__ shift_ptr, int row_stride,
-                              const int* __restrict__ cls, float slope, int mode, bf16* __restrict__ out_a,
+                              const int* __restrict__ cls, float slope, bf16* __restrict__ out_a,
                               bf16* __restrict__ out_xu, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = mode ? 2 * H : H, OW = mode ? 2 * W : W;
@@ -264,11 +275,11 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
 //   mode 2: g is d/d(pre-LeakyReLU) at 2H x 2W (gate applied upstream): gy = up2^T(g), written to gy_out
 //   mode 3: g is d/dy at 2H x 2W and the normalised tensor is up2(x) (final block): reduce at 2H x 2W
 // ---------------------------------------------------------------------------------------------
+template <int mode>
 __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                      const float* __restrict__ shift_ptr, int row_stride, const int* __restrict__ cls,
-                                     float slope, int mode, bf16* __restrict__ gy_out, float* __restrict__ S, int H, int W,
-                                     int cg) {
+                                     float slope, bf16* __restrict__ gy_out, float* __restrict__ S, int H, int W, int cg) {
   extern __shared__ float sh[];  // [prows][2][C]
   __shared__ Gather gtab[GATHER_MAX];
   const int C = cg * 8;
@@ -381,11 +392,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
 
 // pass 2: gx = rstd * (scale * gy - M1 - xhat * M2) (+ residual).  x_up2: gy/gx live at 2H x 2W and xhat is taken
 // from up2(x) (final block, where the statistics are those of the upsampled tensor)
+template <int x_up2>
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ x,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                     int row_stride, const int* __restrict__ cls, const float* __restrict__ M,
-                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int H, int W, int cg,
-                                    int x_up2) {
+                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = x_up2 ? 2 * H : H, OW = x_up2 ? 2 * W : W;
   const int b = blockIdx.y;
@@ -440,8 +451,8 @@ __global__ void up2_bwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ ou
   build_gather_tables(gtab, H, W, (float)(H - 1) / (float)(2 * H - 1), (float)(W - 1) / (float)(2 * W - 1));
   const long long n = (long long)B * H * W * cg;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % cg);
-    long long t = idx / cg;
+    const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
+    int t = (int)((unsigned)idx / (unsigned)cg);
     const int w = (int)(t % W);
     t /= W;
     const int h = (int)(t % H);
@@ -494,7 +505,16 @@ inline Threads pick_threads(int cg, int max_threads) {
 
 #define SPYR_C8(C) SPYR_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channel count %d must be a multiple of 8", __func__, (int)(C))
 
-extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* stream_) {
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* stream_);
+
+extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* stream) {
+  return bn_stats_launch(x, B, H, W, C, up2, nullptr, sums, stream);
+}
+extern "C" int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums, void* stream) {
+  SPYR_REQUIRE(xu_out != nullptr, "up2_stats: xu_out is NULL");
+  return bn_stats_launch(x, B, H, W, C, 1, xu_out, sums, stream);
+}
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_C8(C);
   const int cg = C / 8;
@@ -504,7 +524,10 @@ extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2,
   const long long npix = (long long)B * H * W * (up2 ? 4 : 1);
   long long want = (npix + t.prows * 16 - 1) / (t.prows * 16);
   const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
-  bn_stats_kernel<<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, up2, sums);
+  if (up2)
+    bn_stats_kernel<1><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, (bf16*)xu_out, sums);
+  else
+    bn_stats_kernel<0><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, (bf16*)xu_out, sums);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -534,9 +557,14 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
   const int cap = (2368 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  bn_act_kernel<<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr,
-                                                                     row_stride, cls, slope, mode, (bf16*)out_a,
-                                                                     (bf16*)out_xu, H, W, cg);
+#define SPYR_BN_ACT(M)                                                                                                  \
+  bn_act_kernel<M><<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr, \
+                                                                        row_stride, cls, slope, (bf16*)out_a,          \
+                                                                        (bf16*)out_xu, H, W, cg)
+  if (mode == 0) SPYR_BN_ACT(0);
+  else if (mode == 1) SPYR_BN_ACT(1);
+  else SPYR_BN_ACT(2);
+#undef SPYR_BN_ACT
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -559,9 +587,14 @@ extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mea
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
-  bn_bwd_reduce_kernel<<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(
-      (const bf16*)g, (const bf16*)x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, mode, (bf16*)gy_out, S, H, W,
-      cg);
+#define SPYR_BN_RED(M)                                                                  \
+  bn_bwd_reduce_kernel<M><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(     \
+      (const bf16*)g, (const bf16*)x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, (bf16*)gy_out, S, H, W, cg)
+  if (mode == 0) SPYR_BN_RED(0);
+  else if (mode == 1) SPYR_BN_RED(1);
+  else if (mode == 2) SPYR_BN_RED(2);
+  else SPYR_BN_RED(3);
+#undef SPYR_BN_RED
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -586,9 +619,12 @@ extern "C" int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mea
   const int cap = (2368 + B - 1) / B;
   if (gxx > cap) gxx = cap;
   if (gxx < 1) gxx = 1;
-  bn_bwd_apply_kernel<<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
-      (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg,
-      x_up2);
+  if (x_up2)
+    bn_bwd_apply_kernel<1><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg);
+  else
+    bn_bwd_apply_kernel<0><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -597,6 +633,7 @@ extern "C" int spyr_up2_bwd(const void* g_hi, void* g_lo, int B, int H, int W, i
   SPYR_C8(C);
   SPYR_REQUIRE(H > 1 && W > 1, "up2_bwd: H,W must be > 1");
   const long long n = (long long)B * H * W * (C / 8);
+  SPYR_N32(n);
   SPYR_REQUIRE(H + W <= GATHER_MAX, "up2_bwd: H + W = %d exceeds the gather table (%d)", H + W, GATHER_MAX);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;  // the tables are built once per block: a few blocks per SM, grid-stride loop

@@ -247,10 +247,18 @@ def generator_forward(G, z, features, masks, class_id, save):
     # final block: up2 -> BN -> LeakyReLU -> conv3x3 -> LeakyReLU -> conv1x1 -> tanh
     Bx, H, W, c5 = x.shape
     bn = G.final_block[1]
-    sums = ops.bn_stats(x, up2=True) if training else None
-    mr = ops.bn_finalize(sums, B * 4 * H * W, c5, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
-                         bn.num_batches_tracked, training)
-    a, _ = ops.bn_act(x, mr, bn.weight.data_ptr(), bn.bias.data_ptr(), 0, None, 2)
+    xu = None
+    if training:
+        # the normalised tensor is up2(x): materialise it once (168 MB at cf=1) -- statistics, activation and both
+        # backward passes then run as plain same-resolution kernels instead of re-interpolating x four times
+        xu, sums = ops.up2_stats(x)
+        mr = ops.bn_finalize(sums, B * 4 * H * W, c5, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked, True)
+        a, _ = ops.bn_act(xu, mr, bn.weight.data_ptr(), bn.bias.data_ptr(), 0, None, 0)
+    else:
+        mr = ops.bn_finalize(None, B * 4 * H * W, c5, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked, False)
+        a, _ = ops.bn_act(x, mr, bn.weight.data_ptr(), bn.bias.data_ptr(), 0, None, 2)
     f3, f5_ = G.final_block[3], G.final_block[5]
     _, a3 = ops.conv(B, 2 * H, 2 * W, c5, [Src(a, st.w("final_block.3"), c5, 3)], bias=f3.bias, want_raw=False,
                      want_act=True)
@@ -261,7 +269,7 @@ def generator_forward(G, z, features, masks, class_id, save):
     ctx = None
     if save:
         ctx = dict(st=st, cls=cls, z=z, f6=f6, f5=f5, m6=m6, m5=m5, h0=h0, h1=h1, h2=h2, a0=a0, blocks=block_ctx,
-                   xf=x, mr=mr, a=a, a3=a3, img=img)
+                   xf=x, xu=xu, mr=mr, a=a, a3=a3, img=img)
     return img, ctx
 
 
@@ -289,14 +297,17 @@ def generator_backward(G, ctx, g_img):
                         dmask_slope=LRELU)
     S = torch.empty((B, 2, c5), dtype=F32, device=dev)
     wp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
-    call("spyr_bn_bwd_reduce", g_pre.data_ptr(), x.data_ptr(), mr.data_ptr(), wp, bp, 0, None, LRELU, 3, None,
-         S.data_ptr(), B, H, W, c5)
+    xu = ctx.get("xu")
+    # training forward: BN ran on the materialised up2(x) -> plain reductions at 2H x 2W; eval forward: x interpolated
+    xs, hs, ws, mode = (xu, 2 * H, 2 * W, 0) if xu is not None else (x, H, W, 3)
+    call("spyr_bn_bwd_reduce", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, bp, 0, None, LRELU, mode, None,
+         S.data_ptr(), B, hs, ws, c5)
     M = torch.empty(2 * c5, dtype=F32, device=dev)
     call("spyr_bn_bwd_finalize", S.data_ptr(), B, c5, float(B * 4 * H * W), wp, 0, None, M.data_ptr(),
          ga.ptr(grad, bn.weight), ga.ptr(grad, bn.bias))
     g_hi = torch.empty_like(g_pre)
-    call("spyr_bn_bwd_apply", g_pre.data_ptr(), x.data_ptr(), mr.data_ptr(), wp, 0, None, M.data_ptr(), None,
-         g_hi.data_ptr(), B, H, W, c5, 1)
+    call("spyr_bn_bwd_apply", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, 0, None, M.data_ptr(), None,
+         g_hi.data_ptr(), B, hs, ws, c5, 0 if xu is not None else 1)
     g = torch.empty_like(x)
     call("spyr_up2_bwd", g_hi.data_ptr(), g.data_ptr(), B, H, W, c5)
     del g_hi, g_pre, g_h3

@@ -267,6 +267,15 @@ def bn_stats(x, up2=False):
     return sums
 
 
+def up2_stats(x):
+    """xu = up2(x) (bilinear, align_corners=True) materialised in BF16 together with its per-channel sum / sum of squares."""
+    B, H, W, Cc = x.shape
+    xu = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
+    sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
+    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), sums.data_ptr())
+    return xu, sums
+
+
 def bn_finalize(sums, count, Cc, eps, momentum, running_mean, running_var, nbt, training):
     mean_rstd = torch.empty(2 * Cc, dtype=F32, device=running_mean.device if running_mean is not None else sums.device)
     call("spyr_bn_finalize", ptr(sums), float(count), Cc, eps, momentum, ptr(running_mean), ptr(running_var), ptr(nbt),
