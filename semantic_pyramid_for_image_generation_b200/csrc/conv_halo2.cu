@@ -385,13 +385,22 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   if (d->H < 16 || d->W < 8 || (d->H % 16) != 0 || (d->W % 8) != 0) return -1;
   if (d->splits > 1 || d->block_n != 0) return -1;
   if (d->y_f32 != nullptr && !d->f32_store) return -1;
-  if (d->Cout < 128 || (d->Cout % 128) != 0) return -1;
+  // Cout == 64 with K-major weights also pairs (each CTA stages 32 of the 64 weight rows: 59 instead of 75 clk of operand
+  // fetch per MMA).  Its MN-major (input-gradient) form would need 64-byte-wide operand rows: single-CTA kernel.
+  bool narrow = d->Cout == 64 && getenv("SPYR_PAIR_NO_N64") == nullptr;
+  bool has3x3 = false;
+  for (int s = 0; s < d->nsrc; ++s) {
+    if (d->src[s].w_mn_major) narrow = false;
+    if (d->src[s].ksize == 3) has3x3 = true;
+  }
+  if (!has3x3) narrow = false;  // thin 1x1 layers are epilogue-bound: the single-CTA kernel's deeper halo ring wins
+  if (!narrow && (d->Cout < 128 || (d->Cout % 128) != 0)) return -1;
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.nsrc = d->nsrc;
   static const bool bn128 = getenv("SPYR_PAIR_BN128") != nullptr;  // experiment: less weight traffic per FLOP
-  const int bn = (d->Cout % 256 == 0 && !(bn128 && d->H % 32 == 0)) ? 256 : 128;  // whole N blocks only (384 = 3 x 128)
+  const int bn = narrow ? 64 : ((d->Cout % 256 == 0 && !(bn128 && d->H % 32 == 0)) ? 256 : 128);  // whole N blocks only
   p.msub = (d->H % 32 == 0 && bn <= 128) ? 2 : 1;
   p.block_n = bn;
   p.bn_cols = bn;
