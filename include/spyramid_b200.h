@@ -116,6 +116,9 @@ int spyr_nchw_to_nhwc(const float* src, const float* mask, float slope, void* ds
 /* gate_x (f32 NCHW, may be NULL): dst *= (gate_x > 0 ? 1 : slope) -- backward of the LeakyReLU at models.py:33 */
 int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slope, float* dst, int B, int C, int HW, void* stream);
 int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream);
+/* dst[t][n][k] = src[taps-1-t][k][n] (bf16): forward weight pack [tap][Cout=K][Cin=N] -> K-major operand of the input
+ * gradient (taps flipped); lets 64-wide input gradients run on the CTA-pair kernel */
+int spyr_weight_transpose_flip(const void* src, void* dst, int taps, int K, int N, void* stream);
 
 /* ---- input pipeline: what the reference's DataLoader workers compute per sample, on the device ----
  * One pyramid level of the mask set of B samples from their descriptors (misc.py:47-67).  `depth` counts levels from the

@@ -546,6 +546,26 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16*
   }
 }
 
+// dst[t][n][k] = src[taps-1-t][k][n]: the packed forward weights [tap][Cout][Cin] re-laid out as the K-major operand of
+// the input-gradient convolution (taps flipped, channel roles swapped).  Only used for 64-wide outputs, where the
+// K-major form lets the CTA-pair kernel run the layer (a few hundred KB at most).
+__global__ void weight_transpose_flip_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int taps, int K, int N) {
+  __shared__ bf16 tile[32][33];
+  const int t = blockIdx.z;
+  const bf16* s = src + (size_t)(taps - 1 - t) * K * N;
+  bf16* d = dst + (size_t)t * N * K;
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    if (k < K && n < N) tile[r][threadIdx.x] = s[(size_t)k * N + n];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < K) d[(size_t)n * K + k] = tile[threadIdx.x][r];
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) dst[idx] = __float2bfloat16(src[idx]);
@@ -923,6 +943,14 @@ extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H
   int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
   stencil_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mask, (const bf16*)g, B, H, W, cg, dw, cin_stride,
                                                                       ci_row);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_weight_transpose_flip(const void* src, void* dst, int taps, int K, int N, void* stream) {
+  SPYR_REQUIRE(src && dst && taps > 0 && K > 0 && N > 0, "weight_transpose_flip: bad arguments");
+  dim3 grid(ceil_div(N, 32), ceil_div(K, 32), taps);
+  weight_transpose_flip_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, taps, K, N);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -119,6 +119,15 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
     """out = sum_src conv(src) (+bias, mask stencil, gate, residual).  Returns (y_raw, y_act) (None when not asked).
 
     `w` of a source may be a tensor or an int device address (a slice of a packed-weight arena)."""
+    dev = device or srcs[0].x.device
+    if Cout == 64 and len(srcs) == 1 and srcs[0].mn and srcs[0].ksize == 3 and not srcs[0].per_image and H >= 16 \
+            and f32_out is None and os.environ.get("SPYR_DGRAD_KMAJOR", "1") != "0":
+        # 64-wide input gradient: re-lay the (tiny) forward weights as a K-major operand with flipped taps so the layer
+        # runs on the CTA-pair kernel (its MN-major form is limited to the single-CTA kernel)
+        s0 = srcs[0]
+        wt = torch.empty((9, Cout, s0.cin), dtype=BF16, device=dev)
+        call("spyr_weight_transpose_flip", s0.w if isinstance(s0.w, int) else s0.w.data_ptr(), wt.data_ptr(), 9, s0.cin, Cout)
+        srcs = [Src(s0.x, wt, s0.cin, 3)]
     d = N.ConvDesc()
     d.B, d.H, d.W, d.Cout, d.nsrc = B, H, W, Cout, len(srcs)
     for i, s in enumerate(srcs):
@@ -126,7 +135,6 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         d.src[i].w = s.w if isinstance(s.w, int) else s.w.data_ptr()
         d.src[i].cin, d.src[i].ksize = s.cin, s.ksize
         d.src[i].w_mn_major, d.src[i].w_per_image = int(s.mn), int(s.per_image)
-    dev = device or srcs[0].x.device
     d.bias = bias if isinstance(bias, int) else ptr(bias)
     d.bias2, d.bias3 = ptr(bias2), ptr(bias3)
     d.stencil_mask = ptr(stencil_mask)
