@@ -120,6 +120,15 @@ int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, i
  * gradient (taps flipped); lets 64-wide input gradients run on the CTA-pair kernel */
 int spyr_weight_transpose_flip(const void* src, void* dst, int taps, int K, int N, void* stream);
 
+/* ---- VGG-16 fine-tuning (vgg_16_train.py:134-165): what the frozen-encoder path did not need ----
+ * weight gradient from the tensor-core layout gw[(t*cin_stride + ci)*Cout + co] to the parameter's (Cout,Cin,kh,kw) */
+int spyr_wgrad_to_oihw(const float* gw, float* out, int taps, int Cin, int Cout, int cin_stride, int accumulate, void* stream);
+/* nn.Dropout of the torchvision classifier: y = keep ? x / (1-p) : 0, keep mask (u8) saved for the backward;
+ * counter-based generator keyed by (seed, offset + element index) */
+int spyr_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset, float* y,
+                     void* y_bf16, unsigned char* mask, void* stream);
+int spyr_dropout_bwd(const float* g, const unsigned char* mask, long long n, float p, float* out, void* stream);
+
 /* ---- input pipeline: what the reference's DataLoader workers compute per sample, on the device ----
  * One pyramid level of the mask set of B samples from their descriptors (misc.py:47-67).  `depth` counts levels from the
  * deepest (0 = logits (365), 1 = fc7 (4096), 2 = 8x8 ... 6 = 128x128); vector levels use H = 1.  stage[b] is the kept

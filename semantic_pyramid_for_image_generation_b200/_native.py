@@ -112,6 +112,9 @@ _SIGNATURES = {
     "spyr_diversity_fwd": [P, c_ll, P, c_ll, P, P, P],
     "spyr_diversity_bwd": [P, c_ll, P, P, P, P],
     "spyr_add_inplace": [P, P, c_ll, P],
+    "spyr_wgrad_to_oihw": [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "spyr_dropout_fwd": [P, c_ll, c_float, C.c_ulonglong, C.c_ulonglong, P, P, P, P],
+    "spyr_dropout_bwd": [P, P, c_ll, c_float, P, P],
     "spyr_weight_transpose_flip": [P, P, c_int, c_int, c_int, P],
     "spyr_expand_mask_level": [P, P, P, c_ll, c_int, c_int, c_int, c_int, P, P],
     "spyr_image_u8_minmax_normalize": [P, c_int, c_ll, P, P],

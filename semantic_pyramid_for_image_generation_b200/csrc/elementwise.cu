@@ -566,6 +566,54 @@ __global__ void weight_transpose_flip_kernel(const bf16* __restrict__ src, bf16*
   }
 }
 
+// out[co][ci][t] = gw[(t * cin_stride + ci) * Cout + co]: tensor-core weight gradient ([tap][Cin][Cout], FP32) -> the
+// parameter's own (Cout, Cin, kh, kw) layout.  Spectral-normed layers get this from sn_backward; plain layers (VGG
+// fine-tuning, vgg_16_train.py:164) from here.  ACC: out += (gradient accumulation over batch chunks).
+__global__ void wgrad_to_oihw_kernel(const float* __restrict__ gw, float* __restrict__ out, int taps, int Cin, int Cout,
+                                     int cin_stride, int accumulate) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout) tile[r][threadIdx.x] = gw[((size_t)t * cin_stride + ci) * Cout + co];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < Cin) {
+      float* o = out + ((size_t)co * Cin + ci) * taps + t;
+      *o = accumulate ? *o + tile[threadIdx.x][r] : tile[threadIdx.x][r];
+    }
+  }
+}
+
+// inverted dropout (nn.Dropout, torchvision VGG classifier[2], [5]): keep with probability 1 - p, scale by 1 / (1 - p).
+// Counter-based generator: element i of call (seed, offset) always draws the same number, independent of the launch shape.
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+__global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
+                                   unsigned long long offset, float* __restrict__ y, bf16* __restrict__ y_bf16,
+                                   unsigned char* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float u = (float)(mix32(seed * 0x100000001B3ull + offset + (unsigned long long)i) >> 8) * (1.0f / 16777216.0f);
+  const bool keep = u >= p;
+  const float v = keep ? x[i] / (1.f - p) : 0.f;
+  mask[i] = keep ? 1 : 0;
+  if (y != nullptr) y[i] = v;
+  if (y_bf16 != nullptr) y_bf16[i] = __float2bfloat16(v);
+}
+__global__ void dropout_bwd_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mask, long long n, float p,
+                                   float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mask[i] ? g[i] / (1.f - p) : 0.f;
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) dst[idx] = __float2bfloat16(src[idx]);
@@ -951,6 +999,30 @@ extern "C" int spyr_weight_transpose_flip(const void* src, void* dst, int taps, 
   SPYR_REQUIRE(src && dst && taps > 0 && K > 0 && N > 0, "weight_transpose_flip: bad arguments");
   dim3 grid(ceil_div(N, 32), ceil_div(K, 32), taps);
   weight_transpose_flip_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, taps, K, N);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_wgrad_to_oihw(const float* gw, float* out, int taps, int Cin, int Cout, int cin_stride, int accumulate,
+                                  void* stream) {
+  SPYR_REQUIRE(gw && out && taps > 0 && Cin > 0 && Cout > 0 && cin_stride >= Cin, "wgrad_to_oihw: bad arguments");
+  dim3 grid(ceil_div(Cout, 32), ceil_div(Cin, 32), taps);
+  wgrad_to_oihw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(gw, out, taps, Cin, Cout, cin_stride, accumulate);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset,
+                                float* y, void* y_bf16, unsigned char* mask, void* stream) {
+  SPYR_REQUIRE(x && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments (0 <= p < 1)");
+  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, (bf16*)y_bf16, mask);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int spyr_dropout_bwd(const float* g, const unsigned char* mask, long long n, float p, float* out, void* stream) {
+  SPYR_REQUIRE(g && mask && out && n > 0 && p >= 0.f && p < 1.f, "dropout_bwd: bad arguments (0 <= p < 1)");
+  dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(g, mask, n, p, out);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

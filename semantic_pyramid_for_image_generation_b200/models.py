@@ -317,6 +317,34 @@ class _VGGFn(torch.autograd.Function):
         return None, g_img
 
 
+class _VGGTrainFn(torch.autograd.Function):
+    """Classifier training path (vgg_16_train.py:142-165): logits only, dropout active, gradients for all 32 parameters."""
+
+    @staticmethod
+    def forward(ctx, module, img, dropout, *params):
+        pk = module._pack()
+        _, _, y8, c = vgg_engine.vgg_forward(pk, img, True, dropout=dropout)
+        ctx.module, ctx.pk, ctx.c = module, pk, c
+        return y8
+
+    @staticmethod
+    def backward(ctx, g8):
+        module = ctx.module
+        convs = [module.vgg16.features[i] for i in vgg_engine.CONV_IDX]
+        fcs = [module.vgg16.classifier[i] for i in (0, 3, 6)]
+        new = lambda p: torch.empty_like(p, dtype=torch.float32)
+        wg = {"conv": [(new(m.weight), new(m.bias)) for m in convs], "fc": [(new(m.weight), new(m.bias)) for m in fcs],
+              "keep": [], "image": ctx.needs_input_grad[1]}
+        g_img = vgg_engine.vgg_backward(ctx.pk, ctx.c, [None] * 5, None, g8.contiguous().float(), wg=wg)
+        ctx.c = None
+        by_param = {}
+        for m, (gw, gb) in list(zip(convs, wg["conv"])) + list(zip(fcs, wg["fc"])):
+            by_param[id(m.weight)], by_param[id(m.bias)] = gw, gb
+        grads = tuple(by_param[id(p)] if need else None
+                      for p, need in zip(module.vgg16.parameters(), ctx.needs_input_grad[3:]))
+        return (None, g_img, None) + grads
+
+
 class VGG16(nn.Module):
     '''
     VGG-16 feature pyramid (reference models.py:158-216).  The five spatial taps are returned as NCHW-shaped views of
@@ -336,6 +364,7 @@ class VGG16(nn.Module):
         self.vgg16.classifier = nn.ModuleList(list(self.vgg16.classifier))
         self._pk = None
         self._pk_sig = None
+        self._dropout_calls = 0
 
     def _pack(self):
         sig = tuple((p.data_ptr(), p._version) for p in self.vgg16.parameters())
@@ -351,13 +380,24 @@ class VGG16(nn.Module):
         :return: (List[torch.Tensor]) pool1..pool5 taps, ReLU(fc7), logits
         '''
         _require_cuda(input, "VGG16.forward")
-        if self.training:
-            raise RuntimeError("the B200 VGG16 path is inference-mode only (frozen weights, no dropout); call .eval() "
-                               "as model_wrapper.py:113 does")
         if input.shape[1] == 1:
             input = input.repeat_interleave(3, dim=1)
         if input.dtype != torch.float32 or not input.is_contiguous():
             input = input.float().contiguous()
+        params = list(self.vgg16.parameters())
+        if self.return_output and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # fine-tuning of the encoder as a Places365 classifier (vgg_16_train.py): dropout only in train() mode
+            dropout = None
+            if self.training:
+                p_drop = float(self.vgg16.classifier[2].p)
+                if p_drop > 0.0:
+                    self._dropout_calls += 1
+                    dropout = (p_drop, int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF, self._dropout_calls * (1 << 24))
+            return _VGGTrainFn.apply(self, input, dropout, *params)
+        if self.training:
+            raise RuntimeError("VGG16 in train() mode is the classifier fine-tuning path: construct it with "
+                               "return_output=True and trainable parameters (vgg_16_train.py), or call .eval() as "
+                               "model_wrapper.py:113 does for the frozen feature pyramid")
         outs = _VGGFn.apply(self, input)
         if self.return_output:
             return outs[6]

@@ -1,9 +1,10 @@
-"""VGG-16 feature-pyramid encoder (frozen weights) on the tensor-core conv kernels.
+"""VGG-16 feature-pyramid encoder on the tensor-core conv kernels: frozen for the GAN step, trainable for fine-tuning.
 
 Mirrors VGG16.forward (reference models.py:183-216): ImageNet normalisation of the [-1,1] image as is
 (SURVEY Q8), 13 conv3x3+ReLU, a tap after each of the five max-pools, adaptive 7x7 average pool, fc6 / fc7 / fc8
 with taps at classifier index 3 (which the following in-place ReLU turns into ReLU(fc7)) and 6.
-Weights are frozen (model_wrapper.py:67-68), so they are packed to BF16 once; only input gradients are computed.
+In the GAN step the weights are frozen (model_wrapper.py:67-68): packed to BF16 once, only input gradients computed.
+Fine-tuning (vgg_16_train.py:134-165) adds dropout in the classifier and the weight / bias gradients of all 16 layers.
 """
 import torch
 
@@ -67,8 +68,19 @@ def _fc_forward(x_bf16, w, bias, B, K, O, relu, dev, want_bf16=True):
     return y, yb
 
 
-def vgg_forward(pk, img, save):
-    """img: (B,3,H,W) FP32 NCHW.  Returns ([p1..p5] NHWC BF16, fc7 post-ReLU (B,4096) FP32, logits (B,365) FP32), ctx."""
+def _dropout(y, p, rng):
+    """Inverted dropout of an FP32 activation; returns (y_dropped FP32, BF16 copy, u8 keep mask)."""
+    out, outb = torch.empty_like(y), torch.empty(y.shape, dtype=BF16, device=y.device)
+    mask = torch.empty(y.shape, dtype=torch.uint8, device=y.device)
+    seed, offset = rng
+    call("spyr_dropout_fwd", y.data_ptr(), y.numel(), p, seed, offset, out.data_ptr(), outb.data_ptr(), mask.data_ptr())
+    return out, outb, mask
+
+
+def vgg_forward(pk, img, save, dropout=None):
+    """img: (B,3,H,W) FP32 NCHW.  Returns ([p1..p5] NHWC BF16, fc7 post-ReLU (B,4096) FP32, logits (B,365) FP32), ctx.
+
+    dropout = (p, seed, offset) applies nn.Dropout(p) after ReLU(fc6) and ReLU(fc7) (torchvision classifier[2], [5])."""
     B, Ci, H, W = img.shape
     dev = img.device
     col = torch.empty((B, H, W, 32), dtype=BF16, device=dev)
@@ -89,9 +101,18 @@ def vgg_forward(pk, img, save):
     call("spyr_adaptive_avgpool_fwd", x.data_ptr(), pooled.data_ptr(), B, h, w, 7, 7, c5)
     K6 = 49 * c5
     y6, y6b = _fc_forward(pooled, pk.fc_w[0], pk.fc_b[0], B, K6, pk.fc_w[0].shape[0], True, dev)
+    drop = None
+    x7, x8 = y6, None
+    if dropout is not None:
+        p, seed, offset = dropout
+        x7, y6b, m6 = _dropout(y6, p, (seed, offset))
     y7, y7b = _fc_forward(y6b, pk.fc_w[1], pk.fc_b[1], B, pk.fc_w[1].shape[1], pk.fc_w[1].shape[0], True, dev)
+    x8 = y7
+    if dropout is not None:
+        x8, y7b, m7 = _dropout(y7, p, (seed, offset + y6.numel()))
+        drop = (p, m6, m7, x7, x8)
     y8, _ = _fc_forward(y7b, pk.fc_w[2], pk.fc_b[2], B, pk.fc_w[2].shape[1], pk.n8, False, dev, want_bf16=False)
-    ctx = (col, acts, pools, y6, y7, (B, H, W)) if save else None
+    ctx = (col, acts, pools, y6, y7, (B, H, W), pooled, drop) if save else None
     return pools, y7, y8, ctx
 
 
@@ -102,9 +123,37 @@ def _fc_dgrad(g_bf16, w, B, K, O, dev):
     return acc
 
 
-def vgg_backward(pk, ctx, g_pools, g7, g8):
-    """d/dimage (NCHW FP32) from the gradients of the seven taps (any may be None)."""
-    col, acts, pools, y6, y7, (B, H, W) = ctx
+def _conv_param_grads(wg, j, x_in, g, B, h, w, cin, cout):
+    """Weight and bias gradient of conv j from its input and the gradient of its pre-activation output."""
+    weight, bias = wg["conv"][j]
+    taps, k_in, stride = (1, 32, 27) if j == 0 else (9, cin, cin)
+    gw = torch.zeros(taps * stride * cout, dtype=F32, device=g.device)
+    ops.wgrad(x_in, g, gw.data_ptr(), B, h, w, k_in, cout, 3 if j else 1, cin_stride=stride if j == 0 else 0)
+    if j == 0:
+        # im2col rows k = tap*3 + c  ->  (Cout, 3, 3, 3): nine taps of three channels
+        call("spyr_wgrad_to_oihw", gw.data_ptr(), weight.data_ptr(), 9, 3, cout, 3, 0)
+    else:
+        call("spyr_wgrad_to_oihw", gw.data_ptr(), weight.data_ptr(), 9, cin, cout, cin, 0)
+    bias.zero_()
+    ops.colsum(g, cout, bias.data_ptr())
+    wg["keep"].append(gw)
+
+
+def _fc_param_grads(wg, i, gy, x):
+    """gw[o][k] = sum_b gy[b][o] x[b][k], gb[o] = sum_b gy[b][o] for classifier layer i (batch in chunks of <= 32 rows)."""
+    weight, bias = wg["fc"][i]
+    weight.zero_()
+    bias.zero_()
+    for b0 in range(0, gy.shape[0], 32):
+        ops.linear_bwd_w(gy[b0:b0 + 32].contiguous(), x[b0:b0 + 32].contiguous(), weight.data_ptr(), bias.data_ptr())
+
+
+def vgg_backward(pk, ctx, g_pools, g7, g8, wg=None):
+    """d/dimage (NCHW FP32) from the gradients of the seven taps (any may be None).
+
+    wg (fine-tuning): {"conv": [(weight_grad, bias_grad)] * 13, "fc": [...] * 3, "keep": []} of FP32 tensors in the
+    parameters' own layouts, filled here; the returned image gradient is None when `wg["image"]` is False."""
+    col, acts, pools, y6, y7, (B, H, W), pooled, drop = ctx
     dev = col.device
     c5 = pk.ch[-1][1]
     n7, n6 = y7.shape[1], y6.shape[1]
@@ -122,12 +171,31 @@ def vgg_backward(pk, ctx, g_pools, g7, g8):
             add7 = None
         else:
             add7 = g7.contiguous() if g7 is not None else None
+        if wg is not None and g8 is not None:
+            _fc_param_grads(wg, 2, g8.contiguous(), drop[4] if drop is not None else y7)
+        if drop is not None:
+            # through the dropout that follows ReLU(fc7): d/dy7 = d/dx8 * mask / (1 - p)
+            acc7 = acc7 + add7 if add7 is not None else (acc7.clone() if g8 is None else acc7)
+            add7 = None
+            call("spyr_dropout_bwd", acc7.data_ptr(), drop[2].data_ptr(), acc7.numel(), drop[0], acc7.data_ptr())
         g7b = torch.empty((B, n7), dtype=BF16, device=dev)
+        g7f = torch.empty((B, n7), dtype=F32, device=dev) if wg is not None else None
         call("spyr_vec_epilogue", acc7.data_ptr(), None, add7.data_ptr() if add7 is not None else None, y7.data_ptr(), 2,
-             None, g7b.data_ptr(), n7, B, n7)
+             g7f.data_ptr() if g7f is not None else None, g7b.data_ptr(), n7, B, n7)
+        if wg is not None:
+            _fc_param_grads(wg, 1, g7f, drop[3] if drop is not None else y6)
         acc6 = _fc_dgrad(g7b, pk.fc_w[1], B, n7, n6, dev)
+        if drop is not None:
+            call("spyr_dropout_bwd", acc6.data_ptr(), drop[1].data_ptr(), acc6.numel(), drop[0], acc6.data_ptr())
         g6b = torch.empty((B, n6), dtype=BF16, device=dev)
-        call("spyr_vec_epilogue", acc6.data_ptr(), None, None, y6.data_ptr(), 2, None, g6b.data_ptr(), n6, B, n6)
+        g6f = torch.empty((B, n6), dtype=F32, device=dev) if wg is not None else None
+        call("spyr_vec_epilogue", acc6.data_ptr(), None, None, y6.data_ptr(), 2, g6f.data_ptr() if g6f is not None else None,
+             g6b.data_ptr(), n6, B, n6)
+        if wg is not None:
+            # fc6 reads torch's (C,7,7) flattening: present the pooled map in that order so the gradient lands in the
+            # parameter's own layout
+            x6 = ops.nhwc_to_nchw(pooled).view(B, -1)
+            _fc_param_grads(wg, 0, g6f, x6)
         accp = _fc_dgrad(g6b, pk.fc_w[0], B, n6, 49 * c5, dev)
         g_pooled = ops.cast_bf16(accp).view(B, 7, 7, c5)
         g_pool_in = torch.empty((B, hp, wp, c5), dtype=BF16, device=dev)
@@ -148,7 +216,13 @@ def vgg_backward(pk, ctx, g_pools, g7, g8):
             # g is d/d(pool output): route to the arg-max and gate by the ReLU
             g = ops.maxpool2_bwd(a, g, True)
             level -= 1
+        if wg is not None:
+            # g is now the gradient of conv j's pre-activation output
+            x_in = col if j == 0 else (pools[level] if (j - 1) in POOL_AFTER else acts[j - 1])
+            _conv_param_grads(wg, j, x_in, g, B, h, w, cin, cout)
         if j == 0:
+            if wg is not None and not wg.get("image", True):
+                return None
             g_col, _ = ops.conv(B, h, w, 32, [Src(g, pk.w[0], cout, 1, mn=True)])
             g_img = torch.empty((B, 3, h, w), dtype=F32, device=dev)
             call("spyr_col2im3x3", g_col.data_ptr(), B, h, w, pk.invstd.data_ptr(), g_img.data_ptr(), 0)
