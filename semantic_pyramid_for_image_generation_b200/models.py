@@ -217,7 +217,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         if grad is not None:
             ga, prev = module._ga, module._last_grad_arena
             p0 = ga.params[0]
-            task = torch._C._current_graph_task_id()
+            task = getattr(torch._C, "_current_graph_task_id", lambda: -1)()
             same_pass = prev is not None and task >= 0 and getattr(module, "_grad_task", -1) == task
             earlier_pass = prev is not None and p0.grad is not None and \
                 p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]
