@@ -66,6 +66,7 @@ __global__ void sn_wtu_kernel(const spyr_sn_layer* __restrict__ tab, int n, floa
 }
 
 constexpr int WV_ROWS = 8;  // one weight row per warp
+constexpr int PACK_ROWS = 1;  // weight rows packed per CTA (4 measured slower: 70 vs 52 us, fewer CTAs in flight)
 
 // s[i] = sum_j W[i][j] v[j], v = t / max(|t|, eps) (train) or the stored v (eval); one CTA also stores v
 __global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch, int training,
@@ -151,34 +152,36 @@ __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, con
   }
   if (L.pack_cin <= 0) return;
   const float inv = 1.f / sigma;
-  const int co = tile;
-  const float* wrow = L.w + (size_t)co * L.cols;
   bf16* dst = packed + L.pack_off;
   const int taps = L.taps, pc = L.pack_cin;
-  if (L.pack_mode == 1) {
-    // im2col rows: packed[co][k], k = t*cin + ci, zero padded to pack_cin columns
-    for (int k = threadIdx.x; k < pc; k += blockDim.x) {
+  for (int co = tile * PACK_ROWS; co < min(L.rows, (tile + 1) * PACK_ROWS); ++co) {
+    const float* wrow = L.w + (size_t)co * L.cols;
+    if (L.pack_mode == 1) {
+      // im2col rows: packed[co][k], k = t*cin + ci, zero padded to pack_cin columns
+      for (int k = threadIdx.x; k < pc; k += blockDim.x) {
+        float v = 0.f;
+        if (k < L.cols) v = wrow[(k % L.cin) * taps + k / L.cin] * inv;
+        dst[(size_t)co * pc + k] = __float2bfloat16(v);
+      }
+      continue;
+    }
+    // packed[t][co][ci], ci < pack_cin
+#pragma unroll 4
+    for (int i = threadIdx.x; i < taps * pc; i += blockDim.x) {
+      const int t = i / pc, ci = i % pc;
+      dst[((size_t)t * L.rows + co) * pc + ci] = __float2bfloat16(__ldg(wrow + ci * taps + t) * inv);
+    }
+    if (L.stencil_off >= 0 && threadIdx.x < 32) {
+      // extra (mask) input channel pack_cin: FP32 taps + their sum
+      float* st = stencil + L.stencil_off;
       float v = 0.f;
-      if (k < L.cols) v = wrow[(k % L.cin) * taps + k / L.cin] * inv;
-      dst[(size_t)co * pc + k] = __float2bfloat16(v);
+      if (threadIdx.x < taps) {
+        v = wrow[pc * taps + threadIdx.x] * inv;
+        st[(size_t)threadIdx.x * L.rows + co] = v;
+      }
+      v = warp_sum(v);
+      if (threadIdx.x == 0) st[(size_t)9 * L.rows + co] = v;
     }
-    return;
-  }
-  // packed[t][co][ci], ci < pack_cin
-  for (int i = threadIdx.x; i < taps * pc; i += blockDim.x) {
-    const int t = i / pc, ci = i % pc;
-    dst[((size_t)t * L.rows + co) * pc + ci] = __float2bfloat16(wrow[ci * taps + t] * inv);
-  }
-  if (L.stencil_off >= 0 && threadIdx.x < 32) {
-    // extra (mask) input channel pack_cin: FP32 taps + their sum
-    float* st = stencil + L.stencil_off;
-    float v = 0.f;
-    if (threadIdx.x < taps) {
-      v = wrow[pc * taps + threadIdx.x] * inv;
-      st[(size_t)threadIdx.x * L.rows + co] = v;
-    }
-    v = warp_sum(v);
-    if (threadIdx.x == 0) st[(size_t)9 * L.rows + co] = v;
   }
 }
 
@@ -204,10 +207,23 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
   const float* gw = gw_arena + L.gw_off;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (L.gw_layout == 1) {
-    // coalesced along cout
-    for (int r = wid; r < taps * nci; r += nw) {
-      const int t = r / nci, ci = r - t * nci;
-      if (lane < nco) gsh[t * tstride + ci * (BT + 1) + lane] = gw[((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane];
+    // coalesced along cout.  Each warp owns rows r = wid, wid + nw, ...; four independent 128-byte loads in flight per
+    // warp (a rolled loop has one, which made this kernel latency-bound: 36 dependent round trips per warp).
+    const int nrow = taps * nci;
+    for (int r0 = wid; r0 < nrow; r0 += 4 * nw) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * nw;
+        const int t = r / nci, ci = r - t * nci;
+        v[q] = (r < nrow && lane < nco) ? __ldg(gw + ((size_t)t * L.cin + ci0 + ci) * L.rows + co0 + lane) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * nw;
+        const int t = r / nci, ci = r - t * nci;
+        if (r < nrow && lane < nco) gsh[t * tstride + ci * (BT + 1) + lane] = v[q];
+      }
     }
   } else {
     for (int r = wid; r < nco; r += nw)
@@ -223,6 +239,7 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
     float acc = 0.f;
     for (int r = wid; r < nco; r += nw) {
       const float* wrow = L.w + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
+#pragma unroll 3
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e - ci * taps;
         acc += gsh[t * tstride + ci * (BT + 1) + r] * __ldg(wrow + e);
@@ -238,6 +255,7 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
     for (int r = wid; r < nco; r += nw) {
       const float ur = sv[1 + co0 + r] * coef;
       float* orow = out + (size_t)(co0 + r) * L.cols + (size_t)ci0 * taps;
+#pragma unroll 3
       for (int e = lane; e < nci * taps; e += 32) {
         const int ci = e / taps, t = e - ci * taps;
         orow[e] = (gsh[t * tstride + ci * (BT + 1) + r] - ur * __ldg(vv + e)) * inv;
@@ -280,7 +298,7 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     L.tile0_wv = t_wv;
     t_wv += ceil_div(L.rows, WV_ROWS);
     L.tile0_pack = t_pack;
-    t_pack += L.pack_cin > 0 ? L.rows : 1;
+    t_pack += L.pack_cin > 0 ? ceil_div(L.rows, PACK_ROWS) : 1;
     L.tile0_bwd = t_bwd;
     t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, sn_btc(L.taps));
     L.scratch_off = scratch;  // 16-byte aligned so the power-iteration vector can be read as float4
