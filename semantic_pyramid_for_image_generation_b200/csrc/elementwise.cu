@@ -463,6 +463,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ g, long long rows, int cg
   const int prows = blockDim.x / cg;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
   if (pr < prows)
+#pragma unroll 4  // four independent 16-byte loads in flight per thread (a rolled loop has one)
     for (long long r = (long long)blockIdx.x * prows + pr; r < rows; r += (long long)gridDim.x * prows) {
       ld8(g + (r * cg + c) * 8, a);
 #pragma unroll

@@ -83,8 +83,15 @@ __device__ __forceinline__ Gather gather_src(int j, int in, float scale) {
       ++G.n;
     }
   }
+  // x2 with align_corners gives 3 or 4 taps per low-resolution index: pad to GATHER_TAPS with zero-weight repeats of a
+  // valid position so that the gather loops have a fixed trip count (16 independent loads instead of a rolled loop)
+  for (int k = G.n; k < 8; ++k) {
+    G.o[k] = G.n > 0 ? G.o[G.n - 1] : 0;
+    G.w[k] = 0.f;
+  }
   return G;
 }
+constexpr int GATHER_TAPS = 4;
 
 // Gather tables of one kernel launch in shared memory: rows [0,H) then columns [0,W).  gather_src is ~100 instructions
 // with local arrays; evaluated once per table entry instead of twice per output vector it stops being the cost of the
@@ -130,6 +137,7 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (pr < prows)
+#pragma unroll(up2 ? 1 : 4)  // plain variant: four independent 16-byte loads in flight per thread
     for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
       if (up2) {
         int rowi, ow, b, oh;
@@ -225,6 +233,7 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
   const size_t in_base = (size_t)b * H * W, out_base = (size_t)b * npix;
   const float shs = mode ? (float)(H - 1) / (float)(OH - 1) : 0.f, sws = mode ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const int sh_w = pow2_shift(OW);
+#pragma unroll(mode == 0 ? 4 : 1)
   for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
     float v[8];
     const size_t o = ((out_base + p) * cg + c) * 8;
@@ -306,7 +315,8 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
   const int npix = (mode == 3) ? 4 * H * W : H * W;
   const int sh_w = pow2_shift(W), sh_2w = pow2_shift(2 * W);
   if (pr < prows)
-    for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
+#pragma unroll(mode == 0 ? 4 : 1)
+  for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
       const size_t off = (((size_t)b * npix + p) * cg + c) * 8;
       float xv[8], gy[8];
       if (mode == 3) {
@@ -326,14 +336,35 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
         const Gather& Gw = gtab[H + w];
 #pragma unroll
         for (int j = 0; j < 8; ++j) gy[j] = 0.f;
-        for (int a = 0; a < Gh.n; ++a)
-          for (int e = 0; e < Gw.n; ++e) {
-            float gv[8];
-            ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
-            const float wt = Gh.w[a] * Gw.w[e];
+        if (Gh.n <= GATHER_TAPS && Gw.n <= GATHER_TAPS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gy[j] += wt * gv[j];
+          for (int a = 0; a < GATHER_TAPS; ++a) {
+            uint4 raw[GATHER_TAPS];
+#pragma unroll
+            for (int e = 0; e < GATHER_TAPS; ++e)
+              raw[e] = __ldg(reinterpret_cast<const uint4*>(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8));
+#pragma unroll
+            for (int e = 0; e < GATHER_TAPS; ++e) {
+              const float wt = Gh.w[a] * Gw.w[e];
+              const uint32_t wv[4] = {raw[e].x, raw[e].y, raw[e].z, raw[e].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(wv[j]);
+                gy[2 * j] += wt * f.x;
+                gy[2 * j + 1] += wt * f.y;
+              }
+            }
           }
+        } else {
+          for (int a = 0; a < Gh.n; ++a)
+            for (int e = 0; e < Gw.n; ++e) {
+              float gv[8];
+              ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
+              const float wt = Gh.w[a] * Gw.w[e];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gy[j] += wt * gv[j];
+            }
+        }
         if (mode == 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -419,6 +450,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __r
   const size_t base = (size_t)b * npix;
   const float shs = x_up2 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sws = x_up2 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const int sh_w = pow2_shift(OW);
+#pragma unroll(x_up2 ? 1 : 4)
   for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
     const size_t off = ((base + p) * cg + c) * 8;
     float g[8], xv[8], o[8];
@@ -460,14 +492,35 @@ __global__ void up2_bwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ ou
     const Gather& Gh = gtab[h];
     const Gather& Gw = gtab[H + w];
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int a = 0; a < Gh.n; ++a)
-      for (int e = 0; e < Gw.n; ++e) {
-        float gv[8];
-        ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
-        const float wt = Gh.w[a] * Gw.w[e];
+    if (Gh.n <= GATHER_TAPS && Gw.n <= GATHER_TAPS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += wt * gv[j];
+      for (int a = 0; a < GATHER_TAPS; ++a) {
+        uint4 raw[GATHER_TAPS];
+#pragma unroll
+        for (int e = 0; e < GATHER_TAPS; ++e)
+          raw[e] = __ldg(reinterpret_cast<const uint4*>(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8));
+#pragma unroll
+        for (int e = 0; e < GATHER_TAPS; ++e) {
+          const float wt = Gh.w[a] * Gw.w[e];
+          const uint32_t wv[4] = {raw[e].x, raw[e].y, raw[e].z, raw[e].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(wv[j]);
+            acc[2 * j] += wt * f.x;
+            acc[2 * j + 1] += wt * f.y;
+          }
+        }
       }
+    } else {
+      for (int a = 0; a < Gh.n; ++a)
+        for (int e = 0; e < Gw.n; ++e) {
+          float gv[8];
+          ld8(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, gv);
+          const float wt = Gh.w[a] * Gw.w[e];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += wt * gv[j];
+        }
+    }
     st8(out + idx * 8, acc);
   }
 }
