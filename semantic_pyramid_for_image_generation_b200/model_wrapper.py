@@ -323,6 +323,7 @@ class CapturedTrainingStep(object):
     def __init__(self, wrapper, images_real, labels, masks, w_rec=0.1, w_div=0.1):
         self.w = wrapper
         self.images, self.labels, self.masks = images_real, labels, list(masks)
+        self._stage, self._pending = None, False
         # warm-up on a side stream (allocator, lazy tables, optimizer state), as CUDA-graph capture requires
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -354,7 +355,32 @@ class CapturedTrainingStep(object):
         for dst, src in zip(self.masks, masks):
             dst.copy_(src, non_blocking=True)
 
+    def prefetch(self, images_real, labels, masks) -> None:
+        """Starts the host-to-device copy of the NEXT batch on a copy stream into staging buffers, so that it crosses
+        PCIe while the current iteration computes; the next call moves it into the captured inputs device-to-device
+        (17.9 MB at bs 20: ~10 us instead of ~0.4 ms of PCIe time on the critical path)."""
+        if self._stage is None:
+            self._stage = (torch.empty_like(self.images), torch.empty_like(self.labels),
+                           [torch.empty_like(m) for m in self.masks])
+            self._copy_stream = torch.cuda.Stream(device=self.images.device)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)  # the previous batch has left the staging buffers
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(images_real, non_blocking=True)
+            self._stage[1].copy_(labels, non_blocking=True)
+            for dst, src in zip(self._stage[2], masks):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record(cs)
+        self._pending = True
+
     def __call__(self) -> Dict[str, torch.Tensor]:
+        if self._pending:
+            main = torch.cuda.current_stream()
+            main.wait_event(self._staged)
+            self.load(*self._stage)
+            self._consumed.record(main)
+            self._pending = False
         red = self.w.reducer
         self.graph_a.replay()
         if red is not None and red.active:
