@@ -132,32 +132,47 @@ class ModelWrapper(object):
         main.wait_stream(third)
         return features_real, loss_d_real.detach(), loss_d_fake.detach()
 
-    def _phase_generator(self, features_real, labels, masks, z_g, w_rec, w_div):
-        """D's Adam step, then G, D(fake), the three generator losses, backward.  D acts as a fixed critic here, so its
-        weight gradients are not requested (the reference computes and discards them)."""
-        G, D, V = self.generator, self.discriminator, self.vgg16
+    def _generator_forward(self, features_real, labels, masks, z_g):
+        """The part of the generator phase that does not touch D: under data parallelism it runs while D's gradients are
+        still being all-reduced."""
+        G = self.generator
         batch, device = labels.shape[0], labels.device
-        # D's Adam step (HBM-bound, reads D's gradient arena) only has to finish before D is used again: it shares the GPU
-        # with the generator forward, whose first layers are 4x4 ... 32x32 maps
-        main, side = torch.cuda.current_stream(), self._second_stream(device)
-        if side is not None:
-            side.wait_stream(main)
-        with torch.cuda.stream(side if side is not None else main):
-            self.discriminator_optimizer.step()
         G.zero_grad(set_to_none=True)
-        D.zero_grad(set_to_none=True)
-        _set_requires_grad(D, False)
-        try:
-            if z_g is None:
-                z_g = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
-            images_fake = G(input=z_g, features=features_real, masks=masks, class_id=labels.float())
-            # VGG(fake) on the second stream next to D(fake); autograd runs each backward on its forward's stream, so the
-            # two input-gradient chains overlap as well and meet at images_fake
+        if z_g is None:
+            z_g = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
+        return G(input=z_g, features=features_real, masks=masks, class_id=labels.float()), z_g
+
+    def _phase_generator(self, features_real, labels, masks, z_g, w_rec, w_div, images_fake=None):
+        """D's Adam step, then G, D(fake), the three generator losses, backward.  D acts as a fixed critic here, so its
+        weight gradients are not requested (the reference computes and discards them).  With `images_fake`
+        the generator forward has already run (`_generator_forward`, data-parallel schedule)."""
+        G, D, V = self.generator, self.discriminator, self.vgg16
+        device = labels.device
+        main, side = torch.cuda.current_stream(), self._second_stream(device)
+        overlapped = side if side is not None else main
+        deferred_d_step = images_fake is not None
+        if images_fake is None:
+            # D's Adam step (HBM-bound, reads D's gradient arena) only has to finish before D is used again: it shares the
+            # GPU with the generator forward, whose first layers are 4x4 ... 32x32 maps
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(overlapped):
+                self.discriminator_optimizer.step()
+            D.zero_grad(set_to_none=True)
+            images_fake, z_g = self._generator_forward(features_real, labels, masks, z_g)
             if side is not None:
                 main.wait_stream(side)  # D's new weights
-                side.wait_stream(main)
-            with torch.cuda.stream(side if side is not None else main):
-                features_fake = V(images_fake)
+        # VGG(fake) on the second stream next to D(fake); autograd runs each backward on its forward's stream, so the two
+        # input-gradient chains overlap as well and meet at images_fake
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(overlapped):
+            features_fake = V(images_fake)
+        if deferred_d_step:
+            self.discriminator_optimizer.step()  # data-parallel schedule: after the all-reduce, next to VGG(fake)
+            D.zero_grad(set_to_none=True)
+        _set_requires_grad(D, False)
+        try:
             prediction_fake = D(images_fake, labels)
             loss_g = self.generator_loss(prediction_fake)
             loss_div = w_div * self.diversity_loss(images_fake, z_g)
@@ -175,9 +190,16 @@ class ModelWrapper(object):
         loss scalars as device tensors (no host synchronisation).  `noise` optionally supplies the two latent batches."""
         z_d, z_g = noise if noise is not None else (None, None)
         features_real, loss_d_real, loss_d_fake = self._phase_discriminator(images_real, labels, masks, z_d)
-        if self.reducer is not None:
-            self.reducer.average(self.discriminator)
-        loss_g, loss_rec, loss_div = self._phase_generator(features_real, labels, masks, z_g, w_rec, w_div)
+        if self.reducer is not None and self.reducer.active:
+            # D's gradient all-reduce runs on the collective stream while the generator forward (which does not use D)
+            # runs here; D's Adam step follows the all-reduce
+            self.reducer.average(self.discriminator, wait=False)
+            images_fake, z_g = self._generator_forward(features_real, labels, masks, z_g)
+            self.reducer.wait()
+            loss_g, loss_rec, loss_div = self._phase_generator(features_real, labels, masks, z_g, w_rec, w_div,
+                                                               images_fake=images_fake)
+        else:
+            loss_g, loss_rec, loss_div = self._phase_generator(features_real, labels, masks, z_g, w_rec, w_div)
         if self.reducer is not None:
             self.reducer.average(self.generator)
         self.generator_optimizer.step()
@@ -339,8 +361,20 @@ class CapturedTrainingStep(object):
         with torch.cuda.graph(self.graph_a, pool=pool):
             self.features_real, l_real, l_fake = wrapper._phase_discriminator(self.images, self.labels, self.masks, None)
         self.d_arena = wrapper.discriminator._last_grad_arena
-        with torch.cuda.graph(self.graph_b, pool=pool):
-            l_g, l_rec, l_div = wrapper._phase_generator(self.features_real, self.labels, self.masks, None, w_rec, w_div)
+        self.graph_b1 = None
+        red = wrapper.reducer
+        if red is not None and red.active:
+            # data-parallel schedule: graph B1 (generator forward) overlaps the all-reduce of D's gradients
+            self.graph_b1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b1, pool=pool):
+                images_fake, z_g = wrapper._generator_forward(self.features_real, self.labels, self.masks, None)
+            with torch.cuda.graph(self.graph_b, pool=pool):
+                l_g, l_rec, l_div = wrapper._phase_generator(self.features_real, self.labels, self.masks, z_g, w_rec, w_div,
+                                                             images_fake=images_fake)
+        else:
+            with torch.cuda.graph(self.graph_b, pool=pool):
+                l_g, l_rec, l_div = wrapper._phase_generator(self.features_real, self.labels, self.masks, None, w_rec,
+                                                             w_div)
         self.g_arena = wrapper.generator._last_grad_arena
         with torch.cuda.graph(self.graph_c, pool=pool):
             wrapper.generator_optimizer.step()
@@ -383,8 +417,10 @@ class CapturedTrainingStep(object):
             self._pending = False
         red = self.w.reducer
         self.graph_a.replay()
-        if red is not None and red.active:
-            red.average_flat(self.d_arena)
+        if self.graph_b1 is not None:
+            red.average_flat(self.d_arena, wait=False)
+            self.graph_b1.replay()
+            red.wait()
         self.graph_b.replay()
         if red is not None and red.active:
             red.average_flat(self.g_arena)
