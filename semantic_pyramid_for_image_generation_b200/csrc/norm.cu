@@ -137,7 +137,7 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (pr < prows)
-#pragma unroll(up2 ? 1 : 4)  // plain variant: four independent 16-byte loads in flight per thread
+#pragma unroll(up2 ? 2 : 4)  // independent 16-byte loads in flight per thread: 4 (plain) or 2 x 4 corners (interpolating)
     for (long long p = (long long)blockIdx.x * prows + pr; p < npix; p += (long long)gridDim.x * prows) {
       if (up2) {
         int rowi, ow, b, oh;
@@ -233,7 +233,7 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
   const size_t in_base = (size_t)b * H * W, out_base = (size_t)b * npix;
   const float shs = mode ? (float)(H - 1) / (float)(OH - 1) : 0.f, sws = mode ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const int sh_w = pow2_shift(OW);
-#pragma unroll(mode == 0 ? 4 : 1)
+#pragma unroll(mode == 0 ? 4 : 2)
   for (int p = blockIdx.x * prows + pr; p < npix; p += gridDim.x * prows) {
     float v[8];
     const size_t o = ((out_base + p) * cg + c) * 8;
