@@ -22,7 +22,17 @@ native_tests: $(LIB) build/test_conv_native
 build/test_conv_native: tests/native/test_conv_native.cu $(LIB)
 	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
 
+# developer probes behind the numbers in profiles/r01_mma_probe.txt and r01_tma_probe.txt
+probes: $(LIB) build/mma_probe build/tma_probe
+
+build/mma_probe: tests/native/mma_probe.cu $(CSRC)/common.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $<
+
+build/tma_probe: tests/native/tma_probe.cu $(LIB)
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all native_tests clean
+.PHONY: all native_tests probes clean

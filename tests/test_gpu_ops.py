@@ -494,3 +494,41 @@ def test_fused_sagan_attention_forward(ops, shape):
     assert rel_l2(pm, p_ref) < TOL_BF16
     assert rel_l2(out, o_ref) < TOL_BF16
     assert float((pm.float().sum(-1) - 1).abs().max()) < 2e-2
+
+
+def test_arena_add_and_weight_relayout(ops):
+    """spyr_add_inplace (second D backward pass into the first arena) and spyr_weight_transpose_flip (K-major operand of a
+    64-wide input gradient) are exact data movement / FP32 adds."""
+    from semantic_pyramid_for_image_generation_b200._native import call
+    a = torch.randn(1 << 18, generator=gen(1)).cuda()
+    b = torch.randn(1 << 18, generator=gen(2)).cuda()
+    want = a + b
+    call("spyr_add_inplace", a.data_ptr(), b.data_ptr(), a.numel())
+    assert torch.equal(a, want)
+    w = torch.randn(9, 128, 64, generator=gen(3)).bfloat16().cuda()  # forward pack [tap][Cout=128][Cin=64]
+    out = torch.empty(9, 64, 128, dtype=torch.bfloat16, device="cuda")
+    call("spyr_weight_transpose_flip", w.data_ptr(), out.data_ptr(), 9, 128, 64)
+    assert torch.equal(out, w.flip(0).transpose(1, 2).contiguous())
+
+
+def test_input_gradient_of_64_wide_layer_uses_relaid_weights(ops):
+    """ops.conv routes a 64-wide 3x3 input gradient through the K-major re-lay (CTA-pair kernel); same numbers as the
+    MN-major route of the other widths, checked against torch's conv_transpose."""
+    B, H, W, cin_f, cout_f = 2, 32, 32, 64, 128  # forward conv 64 -> 128; its input gradient has 64 channels
+    g = q(torch.randn(B, cout_f, H, W, generator=gen(4)))
+    w = q(torch.randn(cout_f, cin_f, 3, 3, generator=gen(5)) * 0.05)
+    want = F.conv_transpose2d(g, w, padding=1)
+    got, _ = ops.conv(B, H, W, cin_f, [ops.Src(nhwc(g), pack(w), cout_f, 3, mn=True)])
+    assert rel_l2(nchw(got), want) < TOL_BF16
+
+
+def test_up2_stats_materialises_the_upsampled_map(ops):
+    B, H, W, C = 2, 16, 16, 64
+    x = q(torch.randn(B, C, H, W, generator=gen(6)))
+    xu, sums = ops.up2_stats(nhwc(x))
+    want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    assert tuple(xu.shape) == (B, 2 * H, 2 * W, C)
+    assert rel_l2(nchw(xu), want) < TOL_BF16
+    xs = nchw(xu).double()  # the statistics are those of the stored BF16 values
+    assert torch.allclose(sums[:C].cpu(), xs.sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(sums[C:].cpu(), (xs * xs).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
