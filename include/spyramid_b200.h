@@ -72,6 +72,10 @@ typedef struct {
   int splits;                 /* >=1; >1 requires y_f32 */
   int block_n;                /* 0 = auto, else 32..256 multiple of 16 */
   int stages;                 /* 0 = auto */
+  int pool;                   /* 1: 2x2 average pool fused into the epilogue (nn.AvgPool2d after the second conv of a
+                                 discriminator block, models.py:406,451): y_raw / y_act / residual are NHWC
+                                 [B,H/2,W/2,Cout]; the residual is added after pooling.  Needs Cout % 32 == 0, maps of at
+                                 least 16x8 and none of dmask / stencil / y_f32 / splits */
 } spyr_conv_desc;
 
 int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream);

@@ -331,7 +331,7 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           mk_mode[sub] = all0 ? 0 : (all1 ? 1 : 2);
         }
       }
-      if (p.dmask != nullptr || p.residual != nullptr) {
+      if ((p.dmask != nullptr || p.residual != nullptr) && !p.pool) {
         // the gate / residual operands of this tile are known before its accumulator is: pull them into L2 while the
         // MMAs still run, so the epilogue's loads see L2 latency instead of HBM latency
         for (int sub = 0; sub < p.msub; ++sub) {
@@ -469,6 +469,11 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.act = d->act; p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
   p.epi_mode = epi_mode_for(p);
+  p.pool = d->pool ? 1 : 0;
+  if (p.pool) {
+    SPYR_REQUIRE(p.epi_mode != 0 && p.dmask == nullptr && (d->H % 2) == 0 && (d->W % 2) == 0,
+                 "conv2d_fprop: pool needs Cout %% 32 == 0, BF16 outputs and no gate / stencil (Cout=%d)", d->Cout);
+  }
   const size_t smem_bytes = (size_t)A_BUFS * p.a_buf_bytes + (size_t)stages * p.b_stage_bytes +
                             (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
   static bool configured = false;

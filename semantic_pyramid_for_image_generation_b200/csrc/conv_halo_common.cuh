@@ -24,6 +24,7 @@ struct HaloParams {
   int a_buf_bytes, b_stage_bytes, b_stages;
   int a_bufs;      // halo-tile ring depth (conv_halo.cu; the pair kernel uses A_BUFS)
   int epi_mode;    // 0: generic epilogue_chunk, else a specialised epilogue_chunk_fast (epi_mode_for)
+  int pool;        // 2x2 average pool across lanes in the epilogue; outputs / residual live at (H/2, W/2)
   int tma_store;   // epilogue writes y_raw / y_act through shared-memory staging + TMA stores (maps.y)
   int b_resident;  // conv_halo.cu: every (source, chunk, tap) weight slice of the layer stays in shared memory
   uint32_t tmem_cols;
@@ -283,6 +284,55 @@ __device__ __forceinline__ void epilogue_chunk_fast(const HaloParams& p, const u
   }
 }
 
+// Pooled variant: thread <-> pixel (w = lane & 7, h = lane >> 3 within the warp's 8x4 block), so the 2x2 window of an
+// even (w, h) is lanes {l, l^1, l^8, l^9}: two butterfly adds per value, then the eight even-even lanes hold the pooled
+// pixels of the block and write 64 bytes each.  Saves the full-resolution write and the separate pooling pass.
+template <int OUT, bool RES>
+__device__ __forceinline__ void epilogue_chunk_pool(const HaloParams& p, const uint32_t* r, size_t pooled_off, int lane,
+                                                    uint32_t bias_saddr) {
+  const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
+  float v[32];
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 b = lds128f(bias_saddr + q4 * 16);
+    v[4 * q4] = __uint_as_float(r[4 * q4]) + b.x;
+    v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) + b.y;
+    v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) + b.z;
+    v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) + b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+    v[j] += __shfl_xor_sync(0xffffffffu, v[j], 8);
+    v[j] *= 0.25f;
+  }
+  if ((lane & 9) != 0) return;
+  uint32_t rs[16], oraw[16], oact[16];
+  if (RES) {
+    ldg256(p.residual + pooled_off, rs);
+    ldg256(p.residual + pooled_off + 16, rs + 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float a = v[2 * j], c = v[2 * j + 1];
+    if (RES) {
+      const float2 f = unpack_bf16x2(rs[j]);
+      a += f.x;
+      c += f.y;
+    }
+    if (OUT & 1) oraw[j] = pack_bf16x2(a, c);
+    if (OUT & 2) oact[j] = pack_bf16x2(a > 0.f ? a : a * sl, c > 0.f ? c : c * sl);
+  }
+  if (OUT & 1) {
+    stg256(p.y_raw + pooled_off, oraw);
+    stg256(p.y_raw + pooled_off + 16, oraw + 8);
+  }
+  if (OUT & 2) {
+    stg256(p.y_act + pooled_off, oact);
+    stg256(p.y_act + pooled_off + 16, oact + 8);
+  }
+}
+
 // epi_mode: 0 = generic; otherwise 1 + (OUT - 1) * 4 + DMASK * 2 + RES
 __host__ inline int epi_mode_for(const HaloParams& p) {
   if (p.y_f32 != nullptr || p.stencil_mask != nullptr || p.stencil_w != nullptr || (p.Cout & 31) != 0) return 0;
@@ -293,8 +343,23 @@ __host__ inline int epi_mode_for(const HaloParams& p) {
 
 __device__ __forceinline__ void epilogue_dispatch(const HaloParams& p, const uint32_t* r, size_t pix, int col0, int c0,
                                                   const EpiConst& ec, const float* mk, int mk_mode, const EpiStore& es) {
-  const size_t off0 = pix * p.Cout + col0;
   const uint32_t bs = smem_u32(ec.bias + c0);
+  if (p.pool) {
+    // pix = (n*H + h)*W + w of this lane's pixel -> pooled pixel (n, h/2, w/2); only even-even lanes use the offset
+    const int w = (int)(pix % (size_t)p.W);
+    const size_t row = pix / (size_t)p.W;  // n*H + h
+    const size_t poff = ((row >> 1) * (size_t)(p.W >> 1) + (size_t)(w >> 1)) * p.Cout + col0;
+    switch (p.epi_mode) {
+      case 1: epilogue_chunk_pool<1, false>(p, r, poff, es.lane, bs); break;
+      case 2: epilogue_chunk_pool<1, true>(p, r, poff, es.lane, bs); break;
+      case 5: epilogue_chunk_pool<2, false>(p, r, poff, es.lane, bs); break;
+      case 6: epilogue_chunk_pool<2, true>(p, r, poff, es.lane, bs); break;
+      case 9: epilogue_chunk_pool<3, false>(p, r, poff, es.lane, bs); break;
+      default: epilogue_chunk_pool<3, true>(p, r, poff, es.lane, bs); break;
+    }
+    return;
+  }
+  const size_t off0 = pix * p.Cout + col0;
   switch (p.epi_mode) {
     case 1: epilogue_chunk_fast<1, false, false>(p, r, off0, col0, bs, es); break;
     case 2: epilogue_chunk_fast<1, false, true>(p, r, off0, col0, bs, es); break;

@@ -353,8 +353,13 @@ def _dblock_forward(blk, key, st, x, a, want_act, save):
     c1, c3, cr = blk.main_block[1], blk.main_block[3], blk.residual_mapping
     Cout = c1.shape[0]
     _, h = ops.conv(B, H, W, Cout, [Src(a, st.w(k1), Cin, 3)], bias=c1.bias, want_raw=False, want_act=True)
-    s, _ = ops.conv(B, H, W, Cout, [Src(h, st.w(k3), Cout, 3), Src(x, st.w(kr), Cin, 1)], bias=c3.bias, bias2=cr.bias)
-    out, out_act = ops.avgpool2(s, want_act=want_act)
+    srcs = [Src(h, st.w(k3), Cout, 3), Src(x, st.w(kr), Cin, 1)]
+    if ops.can_pool(H, W, Cout):
+        # AvgPool2d of models.py:451 in the convolution's epilogue: the full-resolution sum is never written
+        out, out_act = ops.conv(B, H, W, Cout, srcs, bias=c3.bias, bias2=cr.bias, want_act=want_act, pool=True)
+    else:
+        s, _ = ops.conv(B, H, W, Cout, srcs, bias=c3.bias, bias2=cr.bias)
+        out, out_act = ops.avgpool2(s, want_act=want_act)
     return out, out_act, ((x, a, h) if save else None)
 
 
@@ -395,12 +400,18 @@ def discriminator_forward(D, img, class_id, save):
     call("spyr_im2col3x3", img.data_ptr(), B, H, W, None, None, col.data_ptr())
     _, h0 = ops.conv(B, H, W, C0, [Src(col, st.w("layers.0.main_block.0"), 32, 1)], bias=c0.bias, want_raw=False,
                      want_act=True)
-    s, _ = ops.conv(B, H, W, C0, [Src(h0, st.w("layers.0.main_block.2"), C0, 3)], bias=c2.bias)
     xp8 = torch.empty((B, H // 2, W // 2, 8), dtype=BF16, device=dev)
     call("spyr_img_avgpool_pad8", img.data_ptr(), B, H, W, xp8.data_ptr())
     r, _ = ops.conv(B, H // 2, W // 2, C0, [Src(xp8, st.w("layers.0.residual_mapping"), 8, 1)], bias=cr.bias)
-    x, a = ops.avgpool2(s, residual=r, want_act=True)
-    del s, r
+    if ops.can_pool(H, W, C0):
+        # avgpool(conv2(...)) + conv1x1(avgpool(x)) (models.py:415-418): pooling and the skip add in conv2's epilogue
+        x, a = ops.conv(B, H, W, C0, [Src(h0, st.w("layers.0.main_block.2"), C0, 3)], bias=c2.bias, residual=r,
+                        want_act=True, pool=True)
+    else:
+        s, _ = ops.conv(B, H, W, C0, [Src(h0, st.w("layers.0.main_block.2"), C0, 3)], bias=c2.bias)
+        x, a = ops.avgpool2(s, residual=r, want_act=True)
+        del s
+    del r
     ctxs = [(col, h0, xp8) if save else None]
     for idx in range(1, 8):
         key = "layers.%d" % idx

@@ -115,8 +115,11 @@ def _run_fprop(d, srcs, B, H, W, Cout, out_bytes):
 
 
 def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=None, stencil_w=None, dmask=None, dmask_slope=1.0, residual=None,
-         want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None):
+         want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None, pool=False):
     """out = sum_src conv(src) (+bias, mask stencil, gate, residual).  Returns (y_raw, y_act) (None when not asked).
+
+    pool=True: 2x2 average pool fused into the epilogue -- outputs (and `residual`) are (B, H/2, W/2, Cout); callers use
+    `can_pool(H, W, Cout)` first (small maps and ragged widths keep the separate pooling kernel).
 
     `w` of a source may be a tensor or an int device address (a slice of a packed-weight arena)."""
     dev = device or srcs[0].x.device
@@ -166,16 +169,25 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
     if f32_out is not None:
         d.y_f32, d.f32_store, d.splits = f32_out.data_ptr(), int(f32_store), splits
     else:
+        oh, ow = (H // 2, W // 2) if pool else (H, W)
+        d.pool = int(pool)
         if want_raw:
-            y_raw = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+            y_raw = torch.empty((B, oh, ow, Cout), dtype=BF16, device=dev)
             d.y_raw = y_raw.data_ptr()
         if want_act:
-            y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+            y_act = torch.empty((B, oh, ow, Cout), dtype=BF16, device=dev)
             d.y_act = y_act.data_ptr()
         d.act, d.act_slope = act, act_slope
     out_bytes = (4 if f32_out is not None else 2) * npix * Cout * (int(want_raw) + int(want_act) if f32_out is None else 1)
     _run_fprop(d, srcs, B, H, W, Cout, out_bytes)
     return y_raw, y_act
+
+
+def can_pool(H, W, Cout):
+    """Whether conv(..., pool=True) applies: a halo-tiled map (>= 16x8, not the split-K small maps) and full 32-channel
+    epilogue chunks."""
+    return H >= 16 and W >= 8 and H % 16 == 0 and W % 8 == 0 and H * W >= 128 and Cout % 32 == 0 \
+        and os.environ.get("SPYR_POOL_FUSION", "1") != "0"
 
 
 def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=False):

@@ -532,3 +532,23 @@ def test_up2_stats_materialises_the_upsampled_map(ops):
     xs = nchw(xu).double()  # the statistics are those of the stored BF16 values
     assert torch.allclose(sums[:C].cpu(), xs.sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
     assert torch.allclose(sums[C:].cpu(), (xs * xs).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64, False), (2, 32, 64, 64, 128, True), (1, 16, 16, 128, 256, True)])
+def test_conv_with_fused_average_pool(ops, shape):
+    """pool=True: avgpool2(conv(x) + bias) (+ residual at the pooled resolution), raw and LeakyReLU outputs, on both the
+    single-CTA (Cout 64, MN... K-major) and the CTA-pair kernels (models.py:406,415-418,451,465)."""
+    B, H, W, cin, cout, with_res = shape
+    assert ops.can_pool(H, W, cout)
+    x = q(torch.randn(B, cin, H, W, generator=gen(7)))
+    w = q(torch.randn(cout, cin, 3, 3, generator=gen(8)) * 0.05)
+    b = torch.randn(cout, generator=gen(9)) * 0.1
+    res = q(torch.randn(B, cout, H // 2, W // 2, generator=gen(10))) if with_res else None
+    want = F.avg_pool2d(F.conv2d(x, w, b, padding=1), 2)
+    if with_res:
+        want = want + res
+    raw, act = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3)], bias=b.cuda(),
+                        residual=nhwc(res) if with_res else None, want_raw=True, want_act=True, pool=True)
+    assert tuple(raw.shape) == (B, H // 2, W // 2, cout)
+    assert rel_l2(nchw(raw), want) < TOL_BF16
+    assert rel_l2(nchw(act), F.leaky_relu(want, 0.2)) < TOL_BF16
