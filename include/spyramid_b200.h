@@ -72,6 +72,9 @@ typedef struct {
   int splits;                 /* >=1; >1 requires y_f32 */
   int block_n;                /* 0 = auto, else 32..256 multiple of 16 */
   int stages;                 /* 0 = auto */
+  int residual_pooled;        /* 1: `residual` is NHWC [B,H/2,W/2,Cout] and enters as 0.25 * residual[h/2][w/2] -- the
+                                 backward of an average-pooled skip branch (models.py:418,465) without materialising
+                                 its full-resolution gradient.  Halo-tiled kernels, Cout % 32 == 0 */
   int pool;                   /* 1: 2x2 average pool fused into the epilogue (nn.AvgPool2d after the second conv of a
                                  discriminator block, models.py:406,451): y_raw / y_act / residual are NHWC
                                  [B,H/2,W/2,Cout]; the residual is added after pooling.  Needs Cout % 32 == 0, maps of at

@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
                 ("bias", c_void_p), ("bias2", c_void_p), ("bias3", c_void_p), ("stencil_mask", c_void_p), ("stencil_w", c_void_p), ("dmask", c_void_p),
                 ("dmask_slope", c_float), ("residual", c_void_p), ("y_raw", c_void_p), ("y_act", c_void_p),
                 ("act", c_int), ("act_slope", c_float), ("y_f32", c_void_p), ("f32_store", c_int), ("splits", c_int),
-                ("block_n", c_int), ("stages", c_int), ("pool", c_int)]
+                ("block_n", c_int), ("stages", c_int), ("residual_pooled", c_int), ("pool", c_int)]
 
 
 class WgradDesc(C.Structure):

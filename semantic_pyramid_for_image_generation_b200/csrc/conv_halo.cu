@@ -285,7 +285,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           mk_mode[sub] = all0 ? 0 : (all1 ? 1 : 2);
         }
       }
-      if ((p.dmask != nullptr || p.residual != nullptr) && !p.pool) {
+      if (p.dmask != nullptr || (p.residual != nullptr && !p.pool && !p.res_pooled)) {
         // the gate / residual operands of this tile are known before its accumulator is: pull them into L2 while the
         // MMAs still run, so the epilogue's loads see L2 latency instead of HBM latency
         for (int sub = 0; sub < p.msub; ++sub) {
@@ -294,7 +294,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
             if (n_off + c0 >= p.Cout) break;
             const size_t off = pix * p.Cout + n_off + c0;
             if (p.dmask != nullptr) prefetch_l2(p.dmask + off);
-            if (p.residual != nullptr) prefetch_l2(p.residual + off);
+            if (p.residual != nullptr && !p.pool && !p.res_pooled) prefetch_l2(p.residual + off);
           }
         }
       }
@@ -459,6 +459,10 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.act = d->act; p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
   p.epi_mode = epi_mode_for(p);
+  p.res_pooled = d->residual_pooled ? 1 : 0;
+  if (p.res_pooled)
+    SPYR_REQUIRE(p.epi_mode != 0 && p.residual != nullptr && !d->pool && (d->H % 2) == 0 && (d->W % 2) == 0,
+                 "conv2d_fprop: residual_pooled needs a residual, Cout %% 32 == 0 and BF16 outputs (Cout=%d)", d->Cout);
   p.pool = d->pool ? 1 : 0;
   if (p.pool) {
     SPYR_REQUIRE(p.epi_mode != 0 && p.dmask == nullptr && (d->H % 2) == 0 && (d->W % 2) == 0,

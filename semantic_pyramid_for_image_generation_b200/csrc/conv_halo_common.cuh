@@ -25,6 +25,7 @@ struct HaloParams {
   int a_bufs;      // halo-tile ring depth (conv_halo.cu; the pair kernel uses A_BUFS)
   int epi_mode;    // 0: generic epilogue_chunk, else a specialised epilogue_chunk_fast (epi_mode_for)
   int pool;        // 2x2 average pool across lanes in the epilogue; outputs / residual live at (H/2, W/2)
+  int res_pooled;  // residual lives at (H/2, W/2) and is added as 0.25 * residual[h/2][w/2]
   int tma_store;   // epilogue writes y_raw / y_act through shared-memory staging + TMA stores (maps.y)
   int b_resident;  // conv_halo.cu: every (source, chunk, tap) weight slice of the layer stays in shared memory
   uint32_t tmem_cols;
@@ -230,15 +231,15 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
 
 template <int OUT, bool DMASK, bool RES>
 __device__ __forceinline__ void epilogue_chunk_fast(const HaloParams& p, const uint32_t* r, size_t off0, int col0,
-                                                    uint32_t bias_saddr, const EpiStore& es) {
+                                                    uint32_t bias_saddr, const EpiStore& es, size_t res_off, float res_scale) {
   uint32_t dm[16], rs[16];
   if (DMASK) {
     ldg256(p.dmask + off0, dm);
     ldg256(p.dmask + off0 + 16, dm + 8);
   }
   if (RES) {
-    ldg256(p.residual + off0, rs);
-    ldg256(p.residual + off0 + 16, rs + 8);
+    ldg256(p.residual + res_off, rs);
+    ldg256(p.residual + res_off + 16, rs + 8);
   }
   const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
   const float gs = p.dmask_slope;
@@ -258,8 +259,8 @@ __device__ __forceinline__ void epilogue_chunk_fast(const HaloParams& p, const u
       }
       if (RES) {
         const float2 f = unpack_bf16x2(rs[2 * q4 + h]);
-        a += f.x;
-        c += f.y;
+        a += res_scale * f.x;
+        c += res_scale * f.y;
       }
       if (OUT & 1) oraw[2 * q4 + h] = pack_bf16x2(a, c);
       if (OUT & 2) {
@@ -360,19 +361,27 @@ __device__ __forceinline__ void epilogue_dispatch(const HaloParams& p, const uin
     return;
   }
   const size_t off0 = pix * p.Cout + col0;
+  size_t ro = off0;
+  float rsc = 1.f;
+  if (p.res_pooled) {
+    const int w = (int)(pix % (size_t)p.W);
+    const size_t row = pix / (size_t)p.W;
+    ro = ((row >> 1) * (size_t)(p.W >> 1) + (size_t)(w >> 1)) * p.Cout + col0;
+    rsc = 0.25f;
+  }
   switch (p.epi_mode) {
-    case 1: epilogue_chunk_fast<1, false, false>(p, r, off0, col0, bs, es); break;
-    case 2: epilogue_chunk_fast<1, false, true>(p, r, off0, col0, bs, es); break;
-    case 3: epilogue_chunk_fast<1, true, false>(p, r, off0, col0, bs, es); break;
-    case 4: epilogue_chunk_fast<1, true, true>(p, r, off0, col0, bs, es); break;
-    case 5: epilogue_chunk_fast<2, false, false>(p, r, off0, col0, bs, es); break;
-    case 6: epilogue_chunk_fast<2, false, true>(p, r, off0, col0, bs, es); break;
-    case 7: epilogue_chunk_fast<2, true, false>(p, r, off0, col0, bs, es); break;
-    case 8: epilogue_chunk_fast<2, true, true>(p, r, off0, col0, bs, es); break;
-    case 9: epilogue_chunk_fast<3, false, false>(p, r, off0, col0, bs, es); break;
-    case 10: epilogue_chunk_fast<3, false, true>(p, r, off0, col0, bs, es); break;
-    case 11: epilogue_chunk_fast<3, true, false>(p, r, off0, col0, bs, es); break;
-    case 12: epilogue_chunk_fast<3, true, true>(p, r, off0, col0, bs, es); break;
+    case 1: epilogue_chunk_fast<1, false, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 2: epilogue_chunk_fast<1, false, true>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 3: epilogue_chunk_fast<1, true, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 4: epilogue_chunk_fast<1, true, true>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 5: epilogue_chunk_fast<2, false, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 6: epilogue_chunk_fast<2, false, true>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 7: epilogue_chunk_fast<2, true, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 8: epilogue_chunk_fast<2, true, true>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 9: epilogue_chunk_fast<3, false, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 10: epilogue_chunk_fast<3, false, true>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 11: epilogue_chunk_fast<3, true, false>(p, r, off0, col0, bs, es, ro, rsc); break;
+    case 12: epilogue_chunk_fast<3, true, true>(p, r, off0, col0, bs, es, ro, rsc); break;
     default: epilogue_chunk(p, r, pix, col0, c0, ec, mk, mk_mode, es); break;
   }
 }

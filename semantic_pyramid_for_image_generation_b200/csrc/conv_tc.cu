@@ -576,7 +576,8 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
       if (rc >= 0) return rc;
     }
   }
-  SPYR_REQUIRE(!d->pool, "conv2d_fprop: the pooled epilogue exists on the halo-tiled kernels only (maps >= 16x8, no split-K)");
+  SPYR_REQUIRE(!d->pool && !d->residual_pooled,
+               "conv2d_fprop: the pooled epilogue / pooled residual exist on the halo-tiled kernels only (maps >= 16x8, no split-K)");
   FpropParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;

@@ -373,13 +373,22 @@ def _dblock_backward(blk, key, st, sn, ga, gw, grad, ctx, g_out, want_wgrad):
     if want_wgrad:
         ops.wgrad(h, g_s, sn.gw_ptr(gw, k3), B, H, W, Cout, Cout, 3)
         ops.wgrad(x, g_s, sn.gw_ptr(gw, kr), B, H, W, Cin, Cout, 1)
-        ops.colsum(g_s, Cout, ga.ptr(grad, c3.bias), ga.ptr(grad, cr.bias))
+        # sum over the full-resolution gradient = sum over the pooled one (each value is replicated 4 x 0.25)
+        ops.colsum(g_out, Cout, ga.ptr(grad, c3.bias), ga.ptr(grad, cr.bias))
     g_h, _ = ops.conv(B, H, W, Cout, [Src(g_s, st.w(k3), Cout, 3, mn=True)], dmask=h, dmask_slope=LRELU)
     if want_wgrad:
         ops.wgrad(a, g_h, sn.gw_ptr(gw, k1), B, H, W, Cin, Cout, 3)
         ops.colsum(g_h, Cout, ga.ptr(grad, c1.bias))
-    g_skip, _ = ops.conv(B, H, W, Cin, [Src(g_s, st.w(kr), Cout, 1, mn=True)])
-    g_x, _ = ops.conv(B, H, W, Cin, [Src(g_h, st.w(k1), Cout, 3, mn=True)], dmask=a, dmask_slope=LRELU, residual=g_skip)
+    if ops.can_pool(H, W, Cin):
+        # the 1x1 skip path is pointwise, so its input gradient commutes with the pooling backward: run it on the pooled
+        # gradient (a quarter of the pixels) and let the main path's epilogue read it as 0.25 * g_skip[h/2][w/2]
+        g_skip, _ = ops.conv(B, H // 2, W // 2, Cin, [Src(g_out, st.w(kr), Cout, 1, mn=True)])
+        g_x, _ = ops.conv(B, H, W, Cin, [Src(g_h, st.w(k1), Cout, 3, mn=True)], dmask=a, dmask_slope=LRELU,
+                          residual=g_skip, residual_pooled=True)
+    else:
+        g_skip, _ = ops.conv(B, H, W, Cin, [Src(g_s, st.w(kr), Cout, 1, mn=True)])
+        g_x, _ = ops.conv(B, H, W, Cin, [Src(g_h, st.w(k1), Cout, 3, mn=True)], dmask=a, dmask_slope=LRELU,
+                          residual=g_skip)
     return g_x
 
 
@@ -480,9 +489,9 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
     g_s = ops.avgpool2_bwd(g)
     if want_wgrad:
         ops.wgrad(h0, g_s, sn.gw_ptr(gw, "layers.0.main_block.2"), B, H, W, C0, C0, 3)
-        ops.colsum(g_s, C0, ga.ptr(grad, c2.bias))
+        # column sums of g_s = those of g (each pooled value replicated 4 x 0.25): one pass serves both biases
+        ops.colsum(g, C0, ga.ptr(grad, c2.bias), ga.ptr(grad, cr.bias))
         ops.wgrad(xp8, g, sn.gw_ptr(gw, "layers.0.residual_mapping"), B, H // 2, W // 2, 8, C0, 1, cin_stride=3)
-        ops.colsum(g, C0, ga.ptr(grad, cr.bias))
     g_h0, _ = ops.conv(B, H, W, C0, [Src(g_s, st.w("layers.0.main_block.2"), C0, 3, mn=True)], dmask=h0,
                        dmask_slope=LRELU)
     del g_s

@@ -115,11 +115,13 @@ def _run_fprop(d, srcs, B, H, W, Cout, out_bytes):
 
 
 def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=None, stencil_w=None, dmask=None, dmask_slope=1.0, residual=None,
-         want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None, pool=False):
+         want_raw=True, want_act=False, act=2, act_slope=LRELU, f32_out=None, f32_store=False, splits=1, device=None, pool=False,
+         residual_pooled=False):
     """out = sum_src conv(src) (+bias, mask stencil, gate, residual).  Returns (y_raw, y_act) (None when not asked).
 
     pool=True: 2x2 average pool fused into the epilogue -- outputs (and `residual`) are (B, H/2, W/2, Cout); callers use
     `can_pool(H, W, Cout)` first (small maps and ragged widths keep the separate pooling kernel).
+    residual_pooled=True: `residual` is (B, H/2, W/2, Cout) and enters as 0.25 * residual[h/2][w/2] (same condition).
 
     `w` of a source may be a tensor or an int device address (a slice of a packed-weight arena)."""
     dev = device or srcs[0].x.device
@@ -144,6 +146,7 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
     d.stencil_w = stencil_w if isinstance(stencil_w, int) else ptr(stencil_w)
     d.dmask, d.dmask_slope = ptr(dmask), dmask_slope
     d.residual = ptr(residual)
+    d.residual_pooled = int(residual_pooled)
     y_raw = y_act = None
     npix = B * H * W
     if f32_out is None and H * W < 128 and Cout % 8 == 0 and not any(s.per_image for s in srcs):

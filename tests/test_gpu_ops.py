@@ -552,3 +552,18 @@ def test_conv_with_fused_average_pool(ops, shape):
     assert tuple(raw.shape) == (B, H // 2, W // 2, cout)
     assert rel_l2(nchw(raw), want) < TOL_BF16
     assert rel_l2(nchw(act), F.leaky_relu(want, 0.2)) < TOL_BF16
+
+
+def test_conv_with_pooled_residual(ops):
+    """residual_pooled=True: out = gate(conv(x)) + 0.25 * upsample_nearest(residual) -- the average-pooled skip branch's
+    gradient joining the main path of a discriminator block without its full-resolution copy."""
+    B, H, W, cin, cout = 2, 32, 32, 128, 64
+    x = q(torch.randn(B, cin, H, W, generator=gen(11)))
+    w = q(torch.randn(cout, cin, 3, 3, generator=gen(12)) * 0.05)
+    gate = q(torch.randn(B, cout, H, W, generator=gen(13)))
+    res = q(torch.randn(B, cout, H // 2, W // 2, generator=gen(14)))
+    want = F.conv2d(x, w, None, padding=1)
+    want = torch.where(gate > 0, want, 0.2 * want) + 0.25 * F.interpolate(res, scale_factor=2, mode="nearest")
+    got, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3)], dmask=nhwc(gate), dmask_slope=0.2,
+                      residual=nhwc(res), residual_pooled=True)
+    assert rel_l2(nchw(got), want) < TOL_BF16
