@@ -137,7 +137,7 @@ def test_modules_mirror_reference_state_dict_layout():
     # Xavier-uniform weights / zero biases / CBN embedding = [1..1|0..0] / gamma = 1
     w = g.main_path[0].main_block[3].weight_orig
     bound = (6.0 / ((w.shape[0] + w.shape[1]) * 9)) ** 0.5
-    assert float(w.abs().max()) <= bound and float(w.abs().max()) > 0.9 * bound
+    assert float(w.abs().max()) <= bound * (1 + 1e-6) and float(w.abs().max()) > 0.9 * bound  # FP32 vs double bound
     assert float(g.main_path[0].main_block[3].bias.abs().max()) == 0.0
     emb = g.main_path[0].main_block[0].embedding.weight
     assert float(emb[:, :512].min()) == 1.0 and float(emb[:, 512:].abs().max()) == 0.0
