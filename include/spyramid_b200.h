@@ -189,7 +189,8 @@ int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, co
  * mode 0: a = lrelu(aff(x));  mode 1: a = up2(lrelu(aff(x))), xu = up2(x);  mode 2: a = lrelu(aff(up2(x))).
  * ------------------------------------------------------------------------------------------------ */
 int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums /* [2C] */, void* stream);
-/* final block (models.py:52-54, upsample -> BN): writes xu = up2(x) (bf16 [B,2H,2W,C]) once and its statistics */
+/* final block (models.py:52-54, upsample -> BN): writes xu = up2(x) (bf16 [B,2H,2W,C]) once and its statistics;
+ * sums may be NULL (plain bilinear x2, align_corners=True: the skip branch of a generator block, models.py:338) */
 int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums /* [2C] */, void* stream);
 int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
                      float* running_var, long long* num_batches_tracked, float* mean_rstd /* [2C] */, int training,

@@ -167,6 +167,7 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
     }
   }
   __syncthreads();
+  if (sums == nullptr) return;  // plain materialisation of up2(x)
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < prows; ++r) s += (double)sh[r * 2 * C + i];
@@ -572,7 +573,7 @@ static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, v
   SPYR_C8(C);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "bn_stats: C=%d too large", C);
-  SPYR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  if (sums != nullptr) SPYR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
   const Threads t = pick_threads(cg, 256);
   const long long npix = (long long)B * H * W * (up2 ? 4 : 1);
   long long want = (npix + t.prows * 16 - 1) / (t.prows * 16);
