@@ -299,14 +299,6 @@ def up2_stats(x):
     return xu, sums
 
 
-def up2(x):
-    """Bilinear x2 (align_corners=True) of an NHWC BF16 map."""
-    B, H, W, Cc = x.shape
-    xu = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
-    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), None)
-    return xu
-
-
 def bn_finalize(sums, count, Cc, eps, momentum, running_mean, running_var, nbt, training):
     mean_rstd = torch.empty(2 * Cc, dtype=F32, device=running_mean.device if running_mean is not None else sums.device)
     call("spyr_bn_finalize", ptr(sums), float(count), Cc, eps, momentum, ptr(running_mean), ptr(running_var), ptr(nbt),
