@@ -19,8 +19,9 @@ $(LIB): $(OBJS)
 
 native_tests: $(LIB) build/test_conv_native
 
-build/test_conv_native: tests/native/test_conv_native.cu $(LIB)
-	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+# halo_probe.cu is a developer probe (descriptor validation of the halo-tiled operand): test-only, never in the product .so
+build/test_conv_native: tests/native/test_conv_native.cu tests/native/halo_probe.cu $(LIB)
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ tests/native/test_conv_native.cu tests/native/halo_probe.cu -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
 
 # developer probes behind the numbers in profiles/r01_mma_probe.txt and r01_tma_probe.txt
 probes: $(LIB) build/mma_probe build/tma_probe

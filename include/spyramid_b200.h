@@ -23,6 +23,24 @@ extern "C" {
 
 const char* spyr_last_error(void);
 int spyr_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Precision mode (process-wide).
+ *   0  BF16 operands, FP32 accumulate (default): every feature map / packed weight is ONE plane of BF16 values.
+ *   1  split BF16 ("strict"): every feature map / packed weight is TWO planes, hi = bf16(v) and lo = bf16(v - hi), the lo
+ *      plane stored directly behind the hi plane (for a map of n elements at p the lo plane starts at p + n).  The tensor
+ *      cores compute x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (three BF16 MMAs, FP32 accumulate), the bandwidth-bound passes
+ *      read hi + lo and write both planes: ~16 mantissa bits end to end, which is what the rel-L2 <= 5e-3 network-level
+ *      parity against the FP32 reference needs.  Callers allocate twice the elements for every BF16 map.
+ *      FP32 tensors (images, vectors, statistics, weight masters, gradients of parameters) are unaffected.
+ * Determinism: no entry point uses floating-point atomics in either mode; grid-wide sums go through caller-provided
+ * scratch (SPYR_REDUCE_SCRATCH_BYTES) and are added in a fixed order, split-K partial sums are separate slices.
+ * ------------------------------------------------------------------------------------------------ */
+int spyr_set_precision(int mode);
+int spyr_get_precision(void);
+/* scratch a deterministic reduction over `n_outputs` values needs (partial vectors of up to 296 blocks, 8-byte slots) */
+#define SPYR_REDUCE_BLOCKS 296
+#define SPYR_REDUCE_SCRATCH_BYTES(n_outputs) ((long long)SPYR_REDUCE_BLOCKS * (long long)(n_outputs) * 8)
 /* number of kernels launched through this library by the calling process (bench.py "gpu_launches") */
 long long spyr_launch_count(void);
 void spyr_launch_count_reset(void);
@@ -36,8 +54,11 @@ void spyr_launch_count_reset(void);
  * followed by the fused epilogue (in this order):
  *   v += bias[co]; v += mask-stencil term; v *= (dmask>0 ? 1 : dmask_slope); v += residual;
  *   y_raw = bf16(v); y_act = bf16(act(v))
- * With y_f32 != NULL the raw accumulator is instead added (red.global.add.f32) to y_f32[pixel][co]
- * (split-K over `splits` CTAs along the reduction; caller zero-fills y_f32 and applies bias/act itself).
+ * With y_f32 != NULL the raw accumulator goes to FP32 memory instead and the caller applies bias / activation itself:
+ *   f32_store = 1: y_f32[pixel][co] = accumulator (one CTA per tile, splits <= 1);
+ *   splits > 1:    split-K -- CTA z of the reduction writes its partial sum to slice z, y_f32[z][pixel][co] (plain
+ *                  stores, every slice fully written, no zero-fill needed); spyr_conv2d_epilogue / spyr_vec_epilogue add
+ *                  the slices in split order, so the result is bit-reproducible (no floating-point atomics).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* x;  /* NHWC bf16 [B,H,W,cin] */
@@ -49,12 +70,16 @@ typedef struct {
                      (UMMA MN-major B operand) and the taps flipped: out[p] = sum_t x[p + d_t] * w[8 - t] */
   int w_per_image;/* 1: ksize must be 1; image b uses weight slice w[b] (batched GEMM for SAGAN attention,
                      models.py:266-268) */
+  long long w_lo_off; /* split-BF16 mode: elements from w to its lo plane; 0 = slices * Cout * cin (the default layout).
+                         Needed when the weight tensor has more rows than Cout (fc8 is stored with 368 rows for 365 classes) */
 } spyr_conv_src;
 
+#define SPYR_CONV_MAX_SRC 9
 typedef struct {
   int B, H, W, Cout;
-  int nsrc;
-  spyr_conv_src src[3];
+  int nsrc;                   /* 1..9 accumulation sources (1..3 in split-BF16 mode, where each source becomes the three
+                                 products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo inside the library) */
+  spyr_conv_src src[SPYR_CONV_MAX_SRC];
   const float* bias;          /* [Cout] or NULL */
   const float* bias2;         /* further bias vectors added in the epilogue (fused residual branches), or NULL */
   const float* bias3;
@@ -67,9 +92,9 @@ typedef struct {
   void* y_act;                /* NHWC bf16 or NULL */
   int act;                    /* 0 none, 1 relu, 2 leaky-relu(act_slope) */
   float act_slope;
-  float* y_f32;               /* f32 [B*H*W][Cout] accumulate target or NULL */
-  int f32_store;              /* 1: plain store of the accumulator to y_f32 (splits must be 1; no zero-fill needed) */
-  int splits;                 /* >=1; >1 requires y_f32 */
+  float* y_f32;               /* f32 [splits][B*H*W][Cout] or NULL */
+  int f32_store;              /* 1: plain store of the accumulator to y_f32 (splits must be 1) */
+  int splits;                 /* >=1; >1 requires y_f32 (one slice per split) */
   int block_n;                /* 0 = auto, else 32..256 multiple of 16 */
   int stages;                 /* 0 = auto */
   int residual_pooled;        /* 1: `residual` is NHWC [B,H/2,W/2,Cout] and enters as 0.25 * residual[h/2][w/2] -- the
@@ -83,13 +108,16 @@ typedef struct {
 
 int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream);
 /* Fused tail of a split-K run: applies the epilogue fields of `d` (biases, stencil, gate, residual, y_raw / y_act) to the
- * FP32 accumulator `acc` [B*H*W][Cout] that spyr_conv2d_fprop(y_f32 = acc, splits > 1) produced.  Used for the 4x4 / 8x8
+ * FP32 partial accumulators `acc` [d->splits][B*H*W][Cout] that spyr_conv2d_fprop(y_f32 = acc, splits > 1) produced.  Used for the 4x4 / 8x8
  * maps, where 3..30 output tiles cannot fill 148 SMs and the reduction dimension is split instead. */
 int spyr_conv2d_epilogue(const spyr_conv_desc* d, const float* acc, void* stream);
 
 /* Weight gradient of the same convolutions (torch autograd conv backward-weight at the call sites above):
- *   dw[tap][ci][co] += sum_{b,h,w} x[b,h+dy,w+dx,ci] * dy[b,h,w,co]     (fp32 red.add; caller zero-fills)
- * Output layout is [taps][Cin][Cout] FP32 ("dgrad-pack order"). */
+ *   dw[tap][ci][co] += sum_{b,h,w} x[b,h+dy,w+dx,ci] * dy[b,h,w,co]
+ * Output layout is [taps][Cin][Cout] FP32 ("dgrad-pack order").  The pixel range is split over CTAs; with more than one
+ * split each CTA stores its partial sum to its own slice of `scratch` and a second kernel adds the slices to dw in slice
+ * order (no floating-point atomics: bit-reproducible).  spyr_conv2d_wgrad_scratch_floats(d) gives the scratch size
+ * (0 = not needed).  In split-BF16 mode x and dy are hi + lo plane pairs and three products are accumulated. */
 typedef struct {
   int B, H, W, Cin, Cout, ksize;
   const void* x;   /* NHWC bf16 [B,H,W,Cin]  */
@@ -103,8 +131,11 @@ typedef struct {
   int per_image;   /* 1: one dw slice per image, dw is f32 [B][taps][Cin][Cout] (attention dK/dV, models.py:266-268) */
   /* debug/validation knobs for the UMMA MN-major descriptors; 0 = defaults */
   int dbg_lbo, dbg_sbo;
+  float* scratch;            /* partial-sum slices, >= spyr_conv2d_wgrad_scratch_floats(d) floats (may be NULL if 0) */
+  long long scratch_floats;
 } spyr_wgrad_desc;
 
+long long spyr_conv2d_wgrad_scratch_floats(const spyr_wgrad_desc* d); /* host only; -1 on a bad descriptor */
 int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -164,23 +195,28 @@ int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, float slope
 /* out = gamma*t + x (models.py:274) and backward (gt = gamma*g, dgamma += <g,t>) */
 int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, void* out_act, float slope,
                             long long n, void* stream);
-int spyr_gamma_residual_bwd(const void* g, const void* t, const float* gamma, void* gt, float* dgamma, long long n, void* stream);
+int spyr_gamma_residual_bwd(const void* g, const void* t, const float* gamma, void* gt, float* dgamma, long long n,
+                            void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(1) */, void* stream);
 /* bias gradients: out_i[c] += sum_rows g[row][c] (out1/out2 may be NULL) */
-int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* stream);
+int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2,
+                void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(C) */, void* stream);
 /* weight gradient of the mask channel of cat(feature*mask, mask): dw[(t*cin_stride+ci_row)*C + co] += ... */
 int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride, int ci_row,
-                       void* stream);
+                       void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(9 * C) */, void* stream);
 int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 /* epilogue of the split-K FC layers (VGG classifier, models.py:210-213) and of their input-gradients:
- * v = acc[b][n] + bias[n] + add[b][n]; mode 1: v = relu(v); mode 2: v *= (gate[b][n] > 0); any pointer may be NULL */
-int spyr_vec_epilogue(const float* acc, const float* bias, const float* add, const float* gate, int mode, float* out_f32,
-                      void* out_bf16, int ld_bf16 /* row stride of out_bf16, >= N */, int B, int N, void* stream);
+ * v = sum_{s < nsplit} acc[s][b][n] (the split-K slices of spyr_conv2d_fprop, summed in split order) + bias[n] + add[b][n];
+ * mode 1: v = relu(v); mode 2: v *= (gate[b][n] > 0); any pointer but acc may be NULL */
+int spyr_vec_epilogue(const float* acc, int nsplit, const float* bias, const float* add, const float* gate, int mode,
+                      float* out_f32, void* out_bf16, int ld_bf16 /* row stride of out_bf16, >= N */, int B, int N,
+                      void* stream);
 /* generator tail: img = tanh(conv1x1(a; W/sigma) + b) -> NCHW f32 (models.py:58-61,99) and its backward, which emits
  * the gradient w.r.t. the PRE-LeakyReLU input of the 1x1 conv (gate from a), dW (w.r.t. W/sigma) and db */
 int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float* sigma, const float* bias, float* img, int B, int HW,
                           int C, int Cout, void* stream);
 int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, const float* w, const float* sigma, float slope,
-                          void* gh, float* dw, float* db, int B, int HW, int C, int Cout, void* stream);
+                          void* gh, float* dw, float* db, int B, int HW, int C, int Cout,
+                          void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(Cout * C + Cout) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (Conditional) batch norm, train-mode statistics, fused with LeakyReLU and bilinear x2 (align_corners=True).
@@ -188,10 +224,12 @@ int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, co
  * Affine convention: scale = scale_ptr[row*row_stride + c], shift = shift_ptr[row*row_stride + c], row = cls[b] or 0.
  * mode 0: a = lrelu(aff(x));  mode 1: a = up2(lrelu(aff(x))), xu = up2(x);  mode 2: a = lrelu(aff(up2(x))).
  * ------------------------------------------------------------------------------------------------ */
-int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums /* [2C] */, void* stream);
+int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums /* [2C] */,
+                  void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C) */, void* stream);
 /* final block (models.py:52-54, upsample -> BN): writes xu = up2(x) (bf16 [B,2H,2W,C]) once and its statistics;
  * sums may be NULL (plain bilinear x2, align_corners=True: the skip branch of a generator block, models.py:338) */
-int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums /* [2C] */, void* stream);
+int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums /* [2C] */,
+                   void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C); may be NULL with sums */, void* stream);
 int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
                      float* running_var, long long* num_batches_tracked, float* mean_rstd /* [2C] */, int training,
                      void* stream);
@@ -199,7 +237,7 @@ int spyr_bn_act(const void* x, const float* mean_rstd, const float* scale_ptr, c
                 const int* cls, float slope, int mode, void* out_a, void* out_xu, int B, int H, int W, int C, void* stream);
 int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr,
                        int row_stride, const int* cls, float slope, int mode, void* gy_out, float* S /* [B][2][C] */, int B,
-                       int H, int W, int C, void* stream);
+                       int H, int W, int C, void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C) */, void* stream);
 int spyr_bn_bwd_finalize(const float* S, int B, int C, float count, const float* scale_ptr, int row_stride, const int* cls,
                          float* M /* [2C] */, float* d_scale, float* d_shift, void* stream);
 int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mean_rstd, const float* scale_ptr, int row_stride,
@@ -218,7 +256,8 @@ typedef struct {
   float* u;              /* weight_u [rows], updated in place in training mode */
   float* v;              /* weight_v [cols] */
   int rows, cols, taps, cin; /* cols = cin * taps */
-  int pack_cin;          /* >0: emit bf16 packed[t][rows][pack_cin] at pack_off; 0: FP32 consumers only need sigma */
+  int pack_cin;          /* >0: emit bf16 packed[t][rows][pack_cin] at pack_off (split-BF16 mode: followed by its lo plane,
+                            so slices must be spaced by twice the elements); 0: FP32 consumers only need sigma */
   int pack_mode;         /* 0: as above.  1: im2col rows packed[rows][pack_cin], k = t*cin + ci, zero padded (3-channel
                             first layers, models.py:393,403) */
   long long pack_off;    /* element offset into the bf16 arena */
@@ -238,7 +277,8 @@ int spyr_sn_plan(spyr_sn_layer* host_tab, int n, spyr_sn_plan_out* out); /* host
 int spyr_sn_forward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, int training, float eps,
                     float* scratch, void* packed, float* stencil, float* saved, void* stream);
 int spyr_sn_backward(const spyr_sn_layer* dev_tab, int n, const spyr_sn_plan_out* plan, const float* gw_arena,
-                     const float* saved, float* dots /* [n] */, float* grad_arena, void* stream);
+                     const float* saved, float* dots /* [plan->tiles_bwd] per-tile partial dot products */, float* grad_arena,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small-batch FP32 linear layers (models.py:28-31,356,360,128,132): y = lrelu_out((f(x) W^T)/sigma + b + y_add),
@@ -270,14 +310,15 @@ int spyr_softmax_rows_bwd(const void* p, const float* dp, void* ds, long long ro
 int spyr_lsgan_fwd(const float* p, long long n, float target, float* out, void* stream);           /* :137,:164 */
 int spyr_lsgan_bwd(const float* p, long long n, float target, const float* gout, float* gp, void* stream);
 int spyr_rec_level_fwd(const void* fr, const void* ff, const float* mask, int B, int H, int W, int C, float* loss,
-                       void* stream);                                                               /* :45-49,67 (loss +=) */
+                       void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(1) */, void* stream);             /* :45-49,67 (loss +=) */
 int spyr_rec_level_bwd(const void* fr, const void* ff, const float* mask, int B, int H, int W, int C, const float* gout,
                        void* gff, void* stream);
-int spyr_rec_vec_fwd(const float* fr, const float* ff, const float* mask, int B, int N, float* loss, void* stream); /* :57-59 */
+int spyr_rec_vec_fwd(const float* fr, const float* ff, const float* mask, int B, int N, float* loss,
+                     void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(1) */, void* stream);               /* :57-59 (loss +=) */
 int spyr_rec_vec_bwd(const float* fr, const float* ff, const float* mask, int B, int N, const float* gout, float* gff,
                      void* stream);
 int spyr_diversity_fwd(const float* img, long long img_half, const float* z, long long z_half, float* work /* [2] */,
-                       float* loss, void* stream);                                                  /* :102-110 */
+                       float* loss, void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2) */, void* stream); /* :102-110 */
 int spyr_diversity_bwd(const float* img, long long img_half, const float* work, const float* gout, float* gimg, void* stream);
 
 /* fused multi-tensor Adam (torch.optim.Adam defaults, main.py:64-65); the step counter lives on the device */

@@ -23,10 +23,35 @@ from . import spyramid_oracle as O
 State = Dict[str, torch.Tensor]
 
 
+ROUNDING = "bf16"  # "bf16": one BF16 plane (8 mantissa bits); "split": hi + lo BF16 planes (~16 bits), the strict mode
+
+
+class rounding(object):
+    """Context manager selecting what the storage points round to: with rounding("split"): ...  The gradient difference
+    between this emulation and the plain FP32 oracle is the sensitivity floor of the network's gradients to forward
+    rounding of that size (non-smooth gates flip), the yardstick printed next to the GPU figures in tests/."""
+
+    def __init__(self, mode):
+        self.mode, self.prev = mode, None
+
+    def __enter__(self):
+        global ROUNDING
+        self.prev, ROUNDING = ROUNDING, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global ROUNDING
+        ROUNDING = self.prev
+        return False
+
+
 class _RoundSTE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return x.bfloat16().float()
+        hi = x.bfloat16().float()
+        if ROUNDING == "split":
+            return hi + (x - hi).bfloat16().float()
+        return hi
 
     @staticmethod
     def backward(ctx, g):

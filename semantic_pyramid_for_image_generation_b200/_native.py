@@ -16,11 +16,11 @@ c_void_p, c_int, c_float, c_ll, c_double = C.c_void_p, C.c_int, C.c_float, C.c_l
 
 class ConvSrc(C.Structure):
     _fields_ = [("x", c_void_p), ("w", c_void_p), ("cin", c_int), ("ksize", c_int), ("w_mn_major", c_int),
-                ("w_per_image", c_int)]
+                ("w_per_image", c_int), ("w_lo_off", c_ll)]
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("Cout", c_int), ("nsrc", c_int), ("src", ConvSrc * 3),
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("Cout", c_int), ("nsrc", c_int), ("src", ConvSrc * 9),
                 ("bias", c_void_p), ("bias2", c_void_p), ("bias3", c_void_p), ("stencil_mask", c_void_p), ("stencil_w", c_void_p), ("dmask", c_void_p),
                 ("dmask_slope", c_float), ("residual", c_void_p), ("y_raw", c_void_p), ("y_act", c_void_p),
                 ("act", c_int), ("act_slope", c_float), ("y_f32", c_void_p), ("f32_store", c_int), ("splits", c_int),
@@ -30,7 +30,8 @@ class ConvDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("ksize", c_int),
                 ("x", c_void_p), ("dy", c_void_p), ("dw", c_void_p), ("cin_stride", c_int), ("splits", c_int),
-                ("stages", c_int), ("per_image", c_int), ("dbg_lbo", c_int), ("dbg_sbo", c_int)]
+                ("stages", c_int), ("per_image", c_int), ("dbg_lbo", c_int), ("dbg_sbo", c_int), ("scratch", c_void_p),
+                ("scratch_floats", c_ll)]
 
 
 class SnLayer(C.Structure):
@@ -76,18 +77,18 @@ _SIGNATURES = {
     "spyr_global_avgpool_lrelu_fwd": [P, c_float, P, c_int, c_int, c_int, P],
     "spyr_global_avgpool_lrelu_bwd": [P, P, c_float, P, c_int, c_int, c_int, P],
     "spyr_gamma_residual_fwd": [P, P, P, P, P, c_float, c_ll, P],
-    "spyr_gamma_residual_bwd": [P, P, P, P, P, c_ll, P],
-    "spyr_colsum": [P, c_ll, c_int, P, P, P, P],
-    "spyr_stencil_wgrad": [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P],
+    "spyr_gamma_residual_bwd": [P, P, P, P, P, c_ll, P, P],
+    "spyr_colsum": [P, c_ll, c_int, P, P, P, P, P],
+    "spyr_stencil_wgrad": [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P],
     "spyr_cast_f32_bf16": [P, P, c_ll, P],
-    "spyr_vec_epilogue": [P, P, P, P, c_int, P, P, c_int, c_int, c_int, P],
+    "spyr_vec_epilogue": [P, c_int, P, P, P, c_int, P, P, c_int, c_int, c_int, P],
     "spyr_conv1x1_tanh_fwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P],
-    "spyr_conv1x1_tanh_bwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
-    "spyr_bn_stats": [P, c_int, c_int, c_int, c_int, c_int, P, P],
-    "spyr_up2_stats": [P, c_int, c_int, c_int, c_int, P, P, P],
+    "spyr_conv1x1_tanh_bwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "spyr_bn_stats": [P, c_int, c_int, c_int, c_int, c_int, P, P, P],
+    "spyr_up2_stats": [P, c_int, c_int, c_int, c_int, P, P, P, P],
     "spyr_bn_finalize": [P, c_double, c_int, c_float, c_float, P, P, P, P, c_int, P],
     "spyr_bn_act": [P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
-    "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
+    "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P, P],
     "spyr_bn_bwd_finalize": [P, c_int, c_int, c_float, P, c_int, P, P, P, P, P],
     "spyr_bn_bwd_apply": [P, P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],  # B,H,W,C,x_up2
     "spyr_up2_bwd": [P, P, c_int, c_int, c_int, c_int, P],
@@ -105,11 +106,11 @@ _SIGNATURES = {
     "spyr_softmax_rows_bwd": [P, P, P, c_ll, c_int, P],
     "spyr_lsgan_fwd": [P, c_ll, c_float, P, P],
     "spyr_lsgan_bwd": [P, c_ll, c_float, P, P, P],
-    "spyr_rec_level_fwd": [P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "spyr_rec_level_fwd": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "spyr_rec_level_bwd": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
-    "spyr_rec_vec_fwd": [P, P, P, c_int, c_int, P, P],
+    "spyr_rec_vec_fwd": [P, P, P, c_int, c_int, P, P, P],
     "spyr_rec_vec_bwd": [P, P, P, c_int, c_int, P, P, P],
-    "spyr_diversity_fwd": [P, c_ll, P, c_ll, P, P, P],
+    "spyr_diversity_fwd": [P, c_ll, P, c_ll, P, P, P, P],
     "spyr_diversity_bwd": [P, c_ll, P, P, P, P],
     "spyr_add_inplace": [P, P, c_ll, P],
     "spyr_wgrad_to_oihw": [P, P, c_int, c_int, c_int, c_int, c_int, P],
@@ -122,7 +123,9 @@ _SIGNATURES = {
     "spyr_adam_step": [C.POINTER(AdamChunk), P, c_float, c_float, c_float, c_float, P],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["spyr_last_error", "spyr_version", "spyr_launch_count",
-                                               "spyr_launch_count_reset"])
+                                               "spyr_launch_count_reset", "spyr_set_precision", "spyr_get_precision",
+                                               "spyr_conv2d_wgrad_scratch_floats"])
+REDUCE_BLOCKS = 296  # SPYR_REDUCE_BLOCKS
 
 _lib = None
 
@@ -140,6 +143,10 @@ def lib():
         handle.spyr_version.restype = c_int
         handle.spyr_launch_count.restype = c_ll
         handle.spyr_launch_count_reset.restype = None
+        handle.spyr_set_precision.argtypes, handle.spyr_set_precision.restype = [c_int], c_int
+        handle.spyr_get_precision.argtypes, handle.spyr_get_precision.restype = [], c_int
+        handle.spyr_conv2d_wgrad_scratch_floats.argtypes = [C.POINTER(WgradDesc)]
+        handle.spyr_conv2d_wgrad_scratch_floats.restype = c_ll
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes

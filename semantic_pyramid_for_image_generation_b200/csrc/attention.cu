@@ -204,6 +204,8 @@ sagan_attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnPara
 
 extern "C" int spyr_sagan_attention_fwd(const void* q, const void* k, const void* v, void* o, void* p_out, int B, int HW,
                                         int d, int nk, int dv, void* stream) {
+  SPYR_REQUIRE(!spyr_split(), "sagan_attention_fwd: the fused kernel computes with single-plane BF16 operands; in split-BF16 "
+               "mode run the attention as per-image GEMMs (spyr_conv2d_fprop with w_per_image) + spyr_softmax_rows_fwd");
   SPYR_REQUIRE(q && k && v && o && B > 0, "sagan_attention_fwd: bad arguments");
   SPYR_REQUIRE(HW % 128 == 0, "sagan_attention_fwd: queries per image (%d) must be a multiple of 128", HW);
   SPYR_REQUIRE(d % 8 == 0 && d >= 8 && d <= 64, "sagan_attention_fwd: query/key width %d must be in 8..64", d);

@@ -15,8 +15,17 @@ void spyr_set_error(const char* fmt, ...) {
 }
 void spyr_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_precision{0};
+bool spyr_split() { return g_precision.load(std::memory_order_relaxed) == 1; }
+
 extern "C" const char* spyr_last_error(void) { return g_err; }
-extern "C" int spyr_version(void) { return 100; }
+extern "C" int spyr_set_precision(int mode) {
+  SPYR_REQUIRE(mode == 0 || mode == 1, "spyr_set_precision: mode %d (0 = BF16 operands, 1 = split BF16 hi+lo)", mode);
+  g_precision.store(mode);
+  return 0;
+}
+extern "C" int spyr_get_precision(void) { return g_precision.load(); }
+extern "C" int spyr_version(void) { return 200; }
 extern "C" long long spyr_launch_count(void) { return g_launches.load(); }
 extern "C" void spyr_launch_count_reset(void) { g_launches.store(0); }
 

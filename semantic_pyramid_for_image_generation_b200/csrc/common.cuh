@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "../../include/spyramid_b200.h"
 
 // ------------------------------------------------------------------------------------------------
 // C-ABI error plumbing: every entry point returns int (0 = ok); message via spyr_last_error().
@@ -217,6 +218,181 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split-BF16 ("strict") precision mode.  spyr_set_precision(1) switches every BF16 feature map and packed weight to a
+// pair of planes: hi = bf16(v), lo = bf16(v - hi), the lo plane stored directly behind the hi plane (at element offset
+// n = number of elements of the map).  Kernels see such a map as an `Act`: a pointer plus the distance of its lo plane
+// (0 in the default single-plane mode).  v is recovered as float(hi) + float(lo) (~16 mantissa bits).
+// ------------------------------------------------------------------------------------------------
+bool spyr_split();  // capi.cu: current precision mode (process-wide)
+
+struct Act {
+  bf16* p;
+  long long lo;  // elements from the hi plane to the lo plane; 0 = single plane
+  __host__ __device__ __forceinline__ Act operator+(long long off) const { return Act{p + off, lo}; }
+  __host__ __device__ __forceinline__ Act operator+(size_t off) const { return Act{p + off, lo}; }
+  __host__ __device__ __forceinline__ Act operator+(int off) const { return Act{p + off, lo}; }
+  __host__ __device__ __forceinline__ bool null() const { return p == nullptr; }
+};
+// host: the map at `ptr` with `n` elements, in the current precision mode
+static inline Act make_act(const void* ptr, long long n) {
+  return Act{reinterpret_cast<bf16*>(const_cast<void*>(ptr)), (ptr != nullptr && spyr_split()) ? n : 0};
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+// 8 consecutive channels of a map -> FP32
+__device__ __forceinline__ void ld8(const bf16* p, float* v) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
+__device__ __forceinline__ void ld8(const Act& a, float* v) {
+  unpack8(*reinterpret_cast<const uint4*>(a.p), v);
+  if (a.lo != 0) {
+    float l[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.p + a.lo), l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += l[j];
+  }
+}
+__device__ __forceinline__ void ld8_nc(const Act& a, float* v) {  // read-only path
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.p)), v);
+  if (a.lo != 0) {
+    float l[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.p + a.lo)), l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += l[j];
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+// residual of the BF16 rounding: lo[j] = v[j] - float(bf16(v[j]))  (exact in FP32)
+__device__ __forceinline__ void split_residual8(const float* v, float* lo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16(v[j]));
+}
+__device__ __forceinline__ void st8(const Act& a, const float* v) {
+  *reinterpret_cast<uint4*>(a.p) = pack8(v);
+  if (a.lo != 0) {
+    float l[8];
+    split_residual8(v, l);
+    *reinterpret_cast<uint4*>(a.p + a.lo) = pack8(l);
+  }
+}
+// what a later pass reads back from a map written with st8: the stored value (BF16, or hi + lo in split mode)
+__device__ __forceinline__ float stored_value(float v, long long lo) {
+  const float h = __bfloat162float(__float2bfloat16(v));
+  return lo != 0 ? h + __bfloat162float(__float2bfloat16(v - h)) : h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic grid-wide reductions: every block writes its partial vector to a caller-provided scratch buffer, the
+// last block to arrive (ticket counter) sums the partials in block order.  No floating-point atomics anywhere, so
+// results are bit-identical from run to run.  Tickets come from a small per-translation-unit pool and reset themselves.
+// ------------------------------------------------------------------------------------------------
+constexpr int SPYR_TICKETS = 4096;
+static __device__ unsigned int spyr_ticket_pool[SPYR_TICKETS];
+// host: next ticket of this translation unit (round robin; a ticket is busy only while its kernel runs)
+static inline unsigned int* spyr_next_ticket() {
+  static unsigned int* base = nullptr;
+  static unsigned int next = 0;
+  if (base == nullptr) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, spyr_ticket_pool) != cudaSuccess) return nullptr;
+    base = reinterpret_cast<unsigned int*>(sym);
+  }
+  return base + (next++ % SPYR_TICKETS);
+}
+// true in exactly one block of the grid: the one that arrives last.  Call with all threads of the block after the block's
+// partial results have been written to global memory.
+__device__ __forceinline__ bool spyr_last_block(unsigned int* ticket, unsigned int nblocks) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == nblocks - 1) ? 1u : 0u;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
+}
+// scalar element access of a map (slow path: layout conversions, 3-channel tails)
+__device__ __forceinline__ float ldf(const Act& a, size_t i) {
+  float v = __bfloat162float(a.p[i]);
+  if (a.lo != 0) v += __bfloat162float(a.p[i + a.lo]);
+  return v;
+}
+__device__ __forceinline__ void stf(const Act& a, size_t i, float v) {
+  const bf16 h = __float2bfloat16(v);
+  a.p[i] = h;
+  if (a.lo != 0) a.p[i + a.lo] = __float2bfloat16(v - __bfloat162float(h));
+}
+// Tail of a deterministic grid reduction, run by the LAST block only (spyr_last_block): sums the partial vectors
+// scratch[b][n], b in [0, nb), in a fixed order and hands each total to sink(i, total).  blockDim.x / n threads share
+// one output (block-strided partial sums combined in lane order), so the summation order depends on the launch shape
+// only.  All threads of the block must call it.
+template <typename T, typename Sink>
+__device__ __forceinline__ void spyr_sum_partials(const T* __restrict__ scratch, int nb, int n, Sink sink) {
+  __shared__ T tmp[1024];
+  const int nt = (int)blockDim.x;
+  int lanes = nt / n;
+  if (lanes < 1) lanes = 1;
+  if (lanes > 16) lanes = 16;
+  const int per_pass = nt / lanes;
+  const int local = (int)threadIdx.x / lanes, lane = (int)threadIdx.x % lanes;
+  for (int i0 = 0; i0 < n; i0 += per_pass) {
+    const int i = i0 + local;
+    T s = (T)0;
+    if (local < per_pass && i < n) {
+#pragma unroll 8
+      for (int b = lane; b < nb; b += lanes) s += __ldcg(scratch + (size_t)b * n + i);
+    }
+    tmp[threadIdx.x] = s;
+    __syncthreads();
+    if (lane == 0 && local < per_pass && i < n) {
+      T t = (T)0;
+      for (int l = 0; l < lanes; ++l) t += tmp[threadIdx.x + l];
+      sink(i, t);
+    }
+    __syncthreads();
+  }
+}
+// SPYR_REDUCE_BLOCKS (include/spyramid_b200.h) bounds the grid of every reduction kernel, and so its scratch
+
+// 32 accumulator columns of one row -> global memory; `ncols` columns are valid.  accumulate: dst += (the row has ONE
+// owner, so a plain read-modify-write is race-free and deterministic); else plain store into a partial-sum slice.
+__device__ __forceinline__ void wgrad_store32(float* dst, const uint32_t* r, int ncols, bool accumulate) {
+  if (ncols >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                             __uint_as_float(r[j + 3]));
+      if (accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(dst + j);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(dst + j) = v;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) dst[j] = accumulate ? dst[j] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+  }
 }
 
 // ---- host: TMA descriptor encode through the runtime's driver entry point (no -lcuda link) ----

@@ -451,7 +451,7 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
       if (spyr_tmap_encode(&maps.w[s], src.w, 3, dims, strides, box, 1)) return 3;
     }
   }
-  for (int s = d->nsrc; s < 3; ++s) {
+  for (int s = d->nsrc; s < SPYR_CONV_MAX_SRC; ++s) {
     maps.x[s] = maps.x[0];
     maps.w[s] = maps.w[0];
   }
@@ -468,6 +468,17 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.y_raw = (bf16*)d->y_raw; p.y_act = (bf16*)d->y_act;
   p.act = d->act; p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
+  p.split = (spyr_split() && d->y_f32 == nullptr) ? 1 : 0;
+  p.y_plane = (long long)d->B * (d->pool ? (d->H / 2) * (d->W / 2) : d->H * d->W) * d->Cout;
+  p.res_plane = p.y_plane;
+  p.acc_scale = 1.f;
+  if (p.split) {
+    int hh_steps = 0;  // (tap, chunk) stages of the hi*hi sources (the last third, see spyr_conv2d_fprop), 4 MMAs each
+    for (int s = 2 * (d->nsrc / 3); s < d->nsrc; ++s) hh_steps += p.kchunks[s] * (p.border[s] ? 9 : 1);
+    p.acc_scale = 1.f + (float)(4 * hh_steps) * 2.9802322e-8f;
+  }
+  SPYR_REQUIRE(!p.split || (!d->pool && !d->residual_pooled),
+               "conv2d_fprop: the pooled epilogue / pooled residual are not available in split-BF16 mode");
   p.epi_mode = epi_mode_for(p);
   p.res_pooled = d->residual_pooled ? 1 : 0;
   if (p.res_pooled)

@@ -15,11 +15,11 @@ struct HaloParams {
   int msub;
   int tiles_w, tiles_h, m_tiles, n_tiles, total_tiles;
   int nsrc;
-  int border[3];   // 1: 3x3 conv, 0: 1x1
-  int kchunks[3];
-  int wmn[3];
-  int wpi[3];
-  int a_rows[3];   // rows (pixels) of the A box of this source
+  int border[SPYR_CONV_MAX_SRC];   // 1: 3x3 conv, 0: 1x1
+  int kchunks[SPYR_CONV_MAX_SRC];
+  int wmn[SPYR_CONV_MAX_SRC];
+  int wpi[SPYR_CONV_MAX_SRC];
+  int a_rows[SPYR_CONV_MAX_SRC];   // rows (pixels) of the A box of this source
   int block_n, bn_cols;  // bn_cols: TMEM column stride of one accumulator (power of two >= 32)
   int a_buf_bytes, b_stage_bytes, b_stages;
   int a_bufs;      // halo-tile ring depth (conv_halo.cu; the pair kernel uses A_BUFS)
@@ -28,6 +28,10 @@ struct HaloParams {
   int res_pooled;  // residual lives at (H/2, W/2) and is added as 0.25 * residual[h/2][w/2]
   int tma_store;   // epilogue writes y_raw / y_act through shared-memory staging + TMA stores (maps.y)
   int b_resident;  // conv_halo.cu: every (source, chunk, tap) weight slice of the layer stays in shared memory
+  int split;       // split-BF16 mode: y_raw / y_act / residual are hi + lo plane pairs (generic epilogue only)
+  long long y_plane, res_plane;  // elements from the hi to the lo plane of the outputs / of the residual
+  float acc_scale;  // split mode: 1 + (hi*hi accumulations per output) * 2^-25 -- the tensor pipe's FP32 accumulator truncates
+                    // on every tcgen05.mma; over a long reduction that is a predictable shrink (tools/probe_split_accum.py)
   uint32_t tmem_cols;
   const float* bias;
   const float* bias2;
@@ -45,8 +49,8 @@ struct HaloParams {
 };
 
 struct HaloMaps {
-  CUtensorMap x[3];
-  CUtensorMap w[3];
+  CUtensorMap x[SPYR_CONV_MAX_SRC];
+  CUtensorMap w[SPYR_CONV_MAX_SRC];
   CUtensorMap y[2];  // y_raw, y_act as (C, W, H, B) with a (32 ch, 8, 4, 1) box, SWIZZLE_64B: epilogue TMA stores
 };
 
@@ -111,7 +115,16 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
   const bool full = col0 + 32 <= p.Cout;
   const bool wide = full && (p.Cout & 15) == 0;  // 32-byte aligned 16-channel groups -> 256-bit LDG/STG
   // issue every global read of this 32-channel chunk before any arithmetic (read-only path, independent of the stores)
-  uint32_t dm[16], rs[16];
+  uint32_t dm[16], rs[16], rl[16];
+  if (p.split && p.residual != nullptr) {
+    // lo plane of the residual (the gate below only needs signs: hi plane)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (col0 + g * 8 + 8 <= p.Cout) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + p.res_plane + off0 + g * 8));
+        rl[4 * g] = u.x; rl[4 * g + 1] = u.y; rl[4 * g + 2] = u.z; rl[4 * g + 3] = u.w;
+      }
+  }
   if (p.dmask != nullptr) {
     if (wide) {
       ldg256(p.dmask + off0, dm);
@@ -140,6 +153,7 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
   }
   const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
   uint32_t oraw[16], oact[16];
+  uint32_t lraw[16], lact[16];  // lo planes (split mode)
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int col = col0 + g * 8;
@@ -147,14 +161,15 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
     float v[8];
     const float4 b0 = *reinterpret_cast<const float4*>(ec.bias + c0 + g * 8);
     const float4 b1 = *reinterpret_cast<const float4*>(ec.bias + c0 + g * 8 + 4);
-    v[0] = __uint_as_float(r[g * 8 + 0]) + b0.x;
-    v[1] = __uint_as_float(r[g * 8 + 1]) + b0.y;
-    v[2] = __uint_as_float(r[g * 8 + 2]) + b0.z;
-    v[3] = __uint_as_float(r[g * 8 + 3]) + b0.w;
-    v[4] = __uint_as_float(r[g * 8 + 4]) + b1.x;
-    v[5] = __uint_as_float(r[g * 8 + 5]) + b1.y;
-    v[6] = __uint_as_float(r[g * 8 + 6]) + b1.z;
-    v[7] = __uint_as_float(r[g * 8 + 7]) + b1.w;
+    const float as = p.split ? p.acc_scale : 1.f;
+    v[0] = __uint_as_float(r[g * 8 + 0]) * as + b0.x;
+    v[1] = __uint_as_float(r[g * 8 + 1]) * as + b0.y;
+    v[2] = __uint_as_float(r[g * 8 + 2]) * as + b0.z;
+    v[3] = __uint_as_float(r[g * 8 + 3]) * as + b0.w;
+    v[4] = __uint_as_float(r[g * 8 + 4]) * as + b1.x;
+    v[5] = __uint_as_float(r[g * 8 + 5]) * as + b1.y;
+    v[6] = __uint_as_float(r[g * 8 + 6]) * as + b1.z;
+    v[7] = __uint_as_float(r[g * 8 + 7]) * as + b1.w;
     if (mk_mode == 1) {
       const float* st = ec.stencil + 9 * p.block_n + c0 + g * 8;
 #pragma unroll
@@ -184,13 +199,46 @@ __device__ __forceinline__ void epilogue_chunk(const HaloParams& p, const uint32
         v[2 * j] += f.x;
         v[2 * j + 1] += f.y;
       }
+      if (p.split) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(rl[4 * g + j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) oraw[4 * g + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    if (p.split) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 h = unpack_bf16x2(oraw[4 * g + j]);
+        lraw[4 * g + j] = pack_bf16x2(v[2 * j] - h.x, v[2 * j + 1] - h.y);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
 #pragma unroll
     for (int j = 0; j < 4; ++j) oact[4 * g + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    if (p.split) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 h = unpack_bf16x2(oact[4 * g + j]);
+        lact[4 * g + j] = pack_bf16x2(v[2 * j] - h.x, v[2 * j + 1] - h.y);
+      }
+    }
+  }
+  if (p.split) {
+    // lo planes: per-thread 16-byte stores (the strict mode is bound by its 3x tensor work, not by this epilogue)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (col0 + g * 8 + 8 > p.Cout) break;
+      if (p.y_raw != nullptr)
+        *reinterpret_cast<uint4*>(p.y_raw + p.y_plane + off0 + g * 8) = make_uint4(lraw[4 * g], lraw[4 * g + 1], lraw[4 * g + 2], lraw[4 * g + 3]);
+      if (p.y_act != nullptr)
+        *reinterpret_cast<uint4*>(p.y_act + p.y_plane + off0 + g * 8) = make_uint4(lact[4 * g], lact[4 * g + 1], lact[4 * g + 2], lact[4 * g + 3]);
+    }
   }
   if (es.maps != nullptr) {
     // channels past Cout (ragged last chunk) hold garbage in o*: the TMA store clips them
@@ -336,6 +384,7 @@ __device__ __forceinline__ void epilogue_chunk_pool(const HaloParams& p, const u
 
 // epi_mode: 0 = generic; otherwise 1 + (OUT - 1) * 4 + DMASK * 2 + RES
 __host__ inline int epi_mode_for(const HaloParams& p) {
+  if (p.split) return 0;  // split-BF16 outputs: generic epilogue only
   if (p.y_f32 != nullptr || p.stencil_mask != nullptr || p.stencil_w != nullptr || (p.Cout & 31) != 0) return 0;
   const int out = (p.y_raw != nullptr ? 1 : 0) | (p.y_act != nullptr ? 2 : 0);
   if (out == 0) return 0;

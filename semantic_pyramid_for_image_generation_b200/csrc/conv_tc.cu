@@ -29,16 +29,17 @@ constexpr int BLOCK_M = 128;  // pixels per CTA tile == TMEM lanes
 constexpr int KC = 64;        // channels per k-step: 64 bf16 = 128 B = one swizzle row
 constexpr int A_BYTES = BLOCK_M * KC * 2;
 
+
 struct FpropParams {
   int B, H, W, Cout;
   int TW, TH, TN;
   int tiles_w, tiles_h;
   int nsrc;
-  int ktaps[3];    // taps per source (1 or 9)
-  int kchunks[3];  // ceil(cin/64) per source
+  int ktaps[SPYR_CONV_MAX_SRC];    // taps per source (1 or 9)
+  int kchunks[SPYR_CONV_MAX_SRC];  // ceil(cin/64) per source
   int ktotal;      // total k-steps
-  int wmn[3];      // source uses the MN-major (input-gradient) weight view
-  int wpi[3];      // source uses per-image weights
+  int wmn[SPYR_CONV_MAX_SRC];      // source uses the MN-major (input-gradient) weight view
+  int wpi[SPYR_CONV_MAX_SRC];      // source uses per-image weights
   int b_bytes;     // bytes reserved for the B tile per stage
   int f32_store;
   int block_n;
@@ -58,11 +59,14 @@ struct FpropParams {
   int act;
   float act_slope;
   float* y_f32;
+  int split;                     // split-BF16 mode: outputs / residual are hi + lo plane pairs
+  long long plane;               // elements from the hi to the lo plane (B*H*W*Cout)
+  float acc_scale;               // split mode: 1 + (hi*hi accumulations) * 2^-25, undoes the accumulator's truncation bias
 };
 
 struct TmapPack {
-  CUtensorMap x[3];
-  CUtensorMap w[3];
+  CUtensorMap x[SPYR_CONV_MAX_SRC];
+  CUtensorMap w[SPYR_CONV_MAX_SRC];
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -117,9 +121,11 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (k_begin < k_end) {
+  // a split of the reduction that got no k-steps still owns a slice of y_f32: its epilogue warps store zeros
+  const bool has_work = k_begin < k_end;
+  if (has_work || p.splits > 1) {
     if (warp == 0) {
-      if (elect_one()) {
+      if (has_work && elect_one()) {
         // ===== TMA producer =====
         // decode k_begin -> (src, tap, chunk)
         int s = 0, rem = k_begin;
@@ -164,7 +170,7 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
           }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && has_work) {
       // ===== MMA issuer =====
       const uint32_t idesc_k = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
       const uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, p.block_n, 0, 1);
@@ -231,40 +237,34 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
         mk_mode = all0 ? 0 : (all1 ? 1 : 2);
       }
 
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
+      if (has_work) {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+      }
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
+        if (has_work) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
         if (!valid) continue;
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;
         if (p.y_f32 != nullptr) {
-          float* dst = p.y_f32 + pix * p.Cout + col0;
-          if (p.f32_store) {
-            if (col0 + 32 <= p.Cout && (p.Cout & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.Cout) dst[j] = __uint_as_float(r[j]);
-            }
-            continue;
-          }
-          if (col0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          // slice blockIdx.z of the split-K partial sums (f32_store: the only slice), plain stores
+          float* dst = p.y_f32 + ((size_t)blockIdx.z * ((size_t)p.B * p.H * p.W) + pix) * p.Cout + col0;
+          if (col0 + 32 <= p.Cout && (p.Cout & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              atomicAdd(reinterpret_cast<float4*>(dst + j),
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                    __uint_as_float(r[j + 3])));
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
+              if (col0 + j < p.Cout) dst[j] = __uint_as_float(r[j]);
           }
           continue;
         }
@@ -274,7 +274,7 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
           if (col + 8 > p.Cout) break;
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.acc_scale;
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += __ldg(&p.bias[col + j]);
@@ -310,34 +310,19 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
               if (!(f.y > 0.f)) v[2 * j + 1] *= p.dmask_slope;
             }
           }
+          const long long lo = p.split ? p.plane : 0;
           if (p.residual != nullptr) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            float rv[8];
+            ld8(Act{const_cast<bf16*>(p.residual) + off, lo}, rv);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(rw[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
+            for (int j = 0; j < 8; ++j) v[j] += rv[j];
           }
-          if (p.y_raw != nullptr) {
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.y_raw + off) = o;
-          }
+          if (p.y_raw != nullptr) st8(Act{p.y_raw + off, lo}, v);
           if (p.y_act != nullptr) {
             const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.y_act + off) = o;
+            st8(Act{p.y_act + off, lo}, v);
           }
         }
       }
@@ -353,7 +338,9 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// wgrad: D[(tap,cin) 128][cout block_n] over a split of the pixel tiles; fp32 red.add to dw[tap][cin][cout]
+// wgrad: D[(tap,cin) 128][cout block_n] over a split of the pixel tiles.  With one split the accumulator is added to
+// dw[tap][cin][cout] directly (each element has one owner); with several, split z stores its partial sum to slice z of a
+// scratch buffer and wgrad_reduce_kernel adds the slices in order -- no floating-point atomics, bit-reproducible.
 // ------------------------------------------------------------------------------------------------
 constexpr int KP = 64;  // pixels per k-step
 
@@ -372,6 +359,8 @@ struct WgradParams {
   int per_image;    // splits per image when > 0 (dw gets one slice per image)
   int cin_stride;   // row stride of dw in input channels
   float* dw;
+  float* partial;   // scratch [slices][nimg][taps*cin_stride*Cout] or nullptr (direct accumulation into dw)
+  int slice0;       // first slice of this launch (split-BF16 mode runs three launches into one slice set)
 };
 
 struct WgradMaps {
@@ -399,8 +388,12 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   const int per = (p.ptiles + p.splits - 1) / p.splits;
   const int k_begin = blockIdx.z * per;
   const int k_end = min(p.ptiles, k_begin + per);
-  float* dw_out = p.dw;
-  if (p.per_image > 0) dw_out += (size_t)(blockIdx.z / p.per_image) * p.taps * p.Cin * p.Cout;
+  const size_t slice_floats = (size_t)p.taps * p.cin_stride * p.Cout;
+  const int img = p.per_image > 0 ? (int)blockIdx.z / p.per_image : 0;
+  const int zz = p.per_image > 0 ? (int)blockIdx.z % p.per_image : (int)blockIdx.z;
+  const int nimg = p.per_image > 0 ? p.B : 1;
+  float* dw_out = p.partial != nullptr ? p.partial + ((size_t)(p.slice0 + zz) * nimg + img) * slice_floats
+                                       : p.dw + (size_t)img * slice_floats;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x);
@@ -503,7 +496,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
       const bool valid_chunk = g < p.mchunks;
       const int tap = valid_chunk ? g / p.cin_chunks : 0;
       const int ci = valid_chunk ? (g % p.cin_chunks) * 64 + (m & 63) : 0;
-      const bool valid = valid_chunk && ci < p.Cin;
+      // rows past the destination's row stride are padding channels of the operand (im2col rows 27..31, the 3 -> 8 channel
+      // pad of the input block's skip path): they have no slot in dw
+      const bool valid = valid_chunk && ci < p.Cin && ci < p.cin_stride;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -513,17 +508,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         if (!valid) continue;
         const int col0 = n_off + c0;
         float* dst = dw_out + ((size_t)tap * p.cin_stride + ci) * p.Cout + col0;
-        if (col0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + j),
-                      make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                  __uint_as_float(r[j + 3])));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
-        }
+        wgrad_store32(dst, r, p.Cout - col0, p.partial == nullptr);
       }
     }
   }
@@ -532,6 +517,31 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dw[img][tap][ci][co] += sum over slices (in slice order) of partial[slice][img][tap][ci][co]; rows ci >= Cin of a
+// strided dw (the mask-channel row of cat(feature*mask, mask)) belong to another kernel and are not touched
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nslices, int nimg, float* __restrict__ dw,
+                                    int taps, int Cin, int cin_stride, int Cout) {
+  const int c4 = Cout >> 2;
+  const long long per_img = (long long)taps * Cin * c4;
+  const long long total = per_img * nimg;
+  const size_t slice_floats = (size_t)taps * cin_stride * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / per_img);
+    long long r = i - (long long)img * per_img;
+    const int co = (int)(r % c4) * 4;
+    r /= c4;
+    const int ci = (int)(r % Cin), tap = (int)(r / Cin);
+    const size_t off = (size_t)img * slice_floats + ((size_t)tap * cin_stride + ci) * Cout + co;
+    float4 acc = *reinterpret_cast<float4*>(dw + off);
+#pragma unroll 4
+    for (int sl = 0; sl < nslices; ++sl) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)sl * nimg * slice_floats + off));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dw + off) = acc;
   }
 }
 
@@ -555,11 +565,45 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
 
+static int conv2d_fprop_impl(const spyr_conv_desc* d, cudaStream_t stream);
+
 extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(d != nullptr, "conv2d_fprop: null descriptor");
-  SPYR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 3, "conv2d_fprop: nsrc=%d out of range", d->nsrc);
   SPYR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "conv2d_fprop: bad shape");
+  if (!spyr_split()) {
+    SPYR_REQUIRE(d->nsrc >= 1 && d->nsrc <= SPYR_CONV_MAX_SRC, "conv2d_fprop: nsrc=%d out of range", d->nsrc);
+    return conv2d_fprop_impl(d, stream);
+  }
+  // split-BF16 mode: x = x_hi + x_lo, w = w_hi + w_lo (lo planes behind the hi planes); every source becomes the three
+  // products x_lo*w_hi + x_hi*w_lo + x_hi*w_hi accumulated in FP32 (x_lo*w_lo is below 2^-17 of the result).
+  // Order matters: the tensor pipe's FP32 accumulator truncates (round toward zero) on every accumulation, a relative
+  // 2^-24 of the CURRENT accumulator magnitude per tcgen05.mma (tools/probe_split_accum.py: a 4608-long reduction with
+  // the large products first shrinks by 2.2e-5).  All small (lo) products therefore go first, while the accumulator is
+  // still 2^-9 of its final size, and the hi*hi products of all sources last: sources [0, 2n) = lo products,
+  // [2n, 3n) = hi*hi.  The launchers compensate the remaining, predictable shrink of the hi*hi chain (acc_scale).
+  SPYR_REQUIRE(d->nsrc >= 1 && 3 * d->nsrc <= SPYR_CONV_MAX_SRC, "conv2d_fprop: nsrc=%d out of range in split-BF16 mode",
+               d->nsrc);
+  spyr_conv_desc e = *d;
+  e.nsrc = 3 * d->nsrc;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const spyr_conv_src& src = d->src[s];
+    const size_t xn = (size_t)d->B * d->H * d->W * src.cin;
+    const size_t wslices = src.w_per_image ? (size_t)d->B : (size_t)(src.ksize * src.ksize);
+    const size_t wn = src.w_lo_off > 0 ? (size_t)src.w_lo_off : wslices * (size_t)d->Cout * src.cin;
+    const bf16* x_hi = (const bf16*)src.x;
+    const bf16* w_hi = (const bf16*)src.w;
+    const int n = d->nsrc;
+    e.src[2 * s] = src;          // x_lo * w_hi
+    e.src[2 * s].x = x_hi + xn;
+    e.src[2 * s + 1] = src;      // x_hi * w_lo
+    e.src[2 * s + 1].w = w_hi + wn;
+    e.src[2 * n + s] = src;      // x_hi * w_hi
+  }
+  return conv2d_fprop_impl(&e, stream);
+}
+
+static int conv2d_fprop_impl(const spyr_conv_desc* d, cudaStream_t stream) {
   SPYR_REQUIRE(is_pow2(d->H) && is_pow2(d->W) || (d->H == 1 && d->W == 1), "conv2d_fprop: H,W must be powers of two");
   {
     // maps of 16x8 pixels and larger run on the persistent halo-tiled kernel (conv_halo.cu); SPYR_CONV_LEGACY=1 forces
@@ -637,11 +681,10 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
       if (spyr_tmap_encode(&maps.w[s], src.w, 3, dims, strides, box, 1)) return 3;
     }
   }
-  for (int s = d->nsrc; s < 3; ++s) {
+  for (int s = d->nsrc; s < SPYR_CONV_MAX_SRC; ++s) {
     maps.x[s] = maps.x[0];
     maps.w[s] = maps.w[0];
   }
-  if (p.splits > p.ktotal) p.splits = p.ktotal;
   const int stage_bytes = A_BYTES + p.b_bytes;
   int stages = d->stages;
   if (stages == 0) {
@@ -664,6 +707,14 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   p.act = d->act;
   p.act_slope = d->act_slope;
   p.y_f32 = d->y_f32;
+  p.split = (spyr_split() && d->y_f32 == nullptr) ? 1 : 0;
+  p.plane = (long long)d->B * d->H * d->W * d->Cout;
+  p.acc_scale = 1.f;
+  if (p.split) {
+    int hh_steps = 0;  // k-steps of the hi*hi sources (the last third, see spyr_conv2d_fprop), 4 accumulations each
+    for (int s = 2 * (d->nsrc / 3); s < d->nsrc; ++s) hh_steps += p.ktaps[s] * p.kchunks[s];
+    p.acc_scale = 1.f + (float)(4 * hh_steps) * 2.9802322e-8f;
+  }
 
   const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   SPYR_REQUIRE(smem_bytes <= 227 * 1024, "conv2d_fprop: smem %zu too large", smem_bytes);
@@ -679,21 +730,13 @@ extern "C" int spyr_conv2d_fprop(const spyr_conv_desc* d, void* stream_) {
   return 0;
 }
 
-extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  SPYR_REQUIRE(d != nullptr, "conv2d_wgrad: null descriptor");
-  SPYR_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv2d_wgrad: ksize must be 1 or 3");
-  SPYR_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "conv2d_wgrad: Cin/Cout must be multiples of 8");
-  SPYR_REQUIRE((is_pow2(d->H) && is_pow2(d->W)) || (d->H == 1 && d->W == 1), "conv2d_wgrad: H,W must be powers of two");
-  {
-    // 3x3 gradients on maps of 16x8 pixels and larger run on the halo-tiled kernel (wgrad_halo.cu)
-    static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
-    if (!legacy) {
-      const int rc = spyr_wgrad_halo_launch(d, stream);
-      if (rc >= 0) return rc;
-    }
-  }
-  WgradParams p;
+// Planning shared by spyr_conv2d_wgrad and spyr_conv2d_wgrad_scratch_floats.
+int spyr_wgrad_halo_plan(const spyr_wgrad_desc* d, int* splits);
+int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, const void* x, const void* dy, float* partial, int slice0,
+                           cudaStream_t stream);
+
+static int wgrad_tc_plan(const spyr_wgrad_desc* d, WgradParams* pp) {
+  WgradParams& p = *pp;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.taps = d->ksize * d->ksize;
@@ -722,6 +765,10 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
     while (s * 2 <= tpi && tpi % (s * 2) == 0 && mtiles * ntiles * d->B * s * 2 <= 2 * 148) s *= 2;
     p.per_image = s;
     splits = d->B * s;
+  } else {
+    // every split must own at least one pixel tile: its slice of the partial sums is read unconditionally
+    const int per = ceil_div(p.ptiles, splits);
+    splits = ceil_div(p.ptiles, per);
   }
   p.splits = splits;
   const int stage_bytes = (2 + bn / 64) * KP * 128;
@@ -737,30 +784,106 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
   p.dw = d->dw;
   p.cin_stride = d->cin_stride > 0 ? d->cin_stride : d->Cin;
   SPYR_REQUIRE(!d->per_image || p.cin_stride == d->Cin, "conv2d_wgrad: per_image cannot use cin_stride");
+  return 0;
+}
 
+static int wgrad_tc_launch(const spyr_wgrad_desc* d, const void* x, const void* dy, float* partial, int slice0,
+                           cudaStream_t stream) {
+  WgradParams p;
+  const int rc = wgrad_tc_plan(d, &p);
+  if (rc) return rc;
+  p.partial = partial;
+  p.slice0 = slice0;
+  const int bn = p.block_n;
   WgradMaps maps;
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    if (spyr_tmap_encode(&maps.x, d->x, 4, dims, strides, box, 1)) return 3;
+    if (spyr_tmap_encode(&maps.x, x, 4, dims, strides, box, 1)) return 3;
   }
   {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t strides[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->W * d->Cout * 2, (uint64_t)d->H * d->W * d->Cout * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    if (spyr_tmap_encode(&maps.dy, d->dy, 4, dims, strides, box, 1)) return 3;
+    if (spyr_tmap_encode(&maps.dy, dy, 4, dims, strides, box, 1)) return 3;
   }
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  const int stage_bytes = (2 + bn / 64) * KP * 128;
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
   SPYR_REQUIRE(smem_bytes <= 227 * 1024, "conv2d_wgrad: smem %zu too large", smem_bytes);
   static bool configured = false;
   if (!configured) {
     SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  dim3 grid(mtiles, ntiles, splits);
+  dim3 grid(ceil_div(p.mchunks, 2), ceil_div(d->Cout, bn), p.splits);
   conv_wgrad_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
+  return 0;
+}
+
+// route: 0 = halo-tiled kernel, 1 = per-tap kernel; *slices = partial-sum slices per image (1: accumulate into dw directly)
+static int wgrad_route(const spyr_wgrad_desc* d, int* route, int* slices) {
+  SPYR_REQUIRE(d != nullptr, "conv2d_wgrad: null descriptor");
+  SPYR_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv2d_wgrad: ksize must be 1 or 3");
+  SPYR_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "conv2d_wgrad: Cin/Cout must be multiples of 8");
+  SPYR_REQUIRE((is_pow2(d->H) && is_pow2(d->W)) || (d->H == 1 && d->W == 1), "conv2d_wgrad: H,W must be powers of two");
+  static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
+  int splits = 0;
+  *route = 1;
+  if (!legacy && spyr_wgrad_halo_plan(d, &splits) == 0) {
+    *route = 0;
+  } else {
+    WgradParams p;
+    const int rc = wgrad_tc_plan(d, &p);
+    if (rc) return rc;
+    splits = p.per_image > 0 ? p.per_image : p.splits;
+  }
+  *slices = splits * (spyr_split() ? 3 : 1);
+  return 0;
+}
+
+extern "C" long long spyr_conv2d_wgrad_scratch_floats(const spyr_wgrad_desc* d) {
+  int route = 0, slices = 0;
+  if (wgrad_route(d, &route, &slices)) return -1;
+  if (slices <= 1) return 0;
+  const long long cs = d->cin_stride > 0 ? d->cin_stride : d->Cin;
+  return (long long)slices * (d->per_image ? d->B : 1) * d->ksize * d->ksize * cs * d->Cout;
+}
+
+extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int route = 0, slices = 0;
+  const int rc0 = wgrad_route(d, &route, &slices);
+  if (rc0) return rc0;
+  const long long need = spyr_conv2d_wgrad_scratch_floats(d);
+  SPYR_REQUIRE(need == 0 || (d->scratch != nullptr && d->scratch_floats >= need),
+               "conv2d_wgrad: scratch of %lld floats needed (spyr_conv2d_wgrad_scratch_floats), got %lld", need,
+               d->scratch != nullptr ? d->scratch_floats : 0LL);
+  float* partial = slices > 1 ? d->scratch : nullptr;
+  // split-BF16 mode: dw = x_hi*dy_hi + x_lo*dy_hi + x_hi*dy_lo, three launches into consecutive slice groups
+  const int nsub = spyr_split() ? 3 : 1;
+  const int per_sub = slices / nsub;
+  const size_t xn = (size_t)d->B * d->H * d->W * d->Cin, yn = (size_t)d->B * d->H * d->W * d->Cout;
+  for (int sub = 0; sub < nsub; ++sub) {
+    const bf16* x = (const bf16*)d->x + (sub == 1 ? xn : 0);
+    const bf16* dy = (const bf16*)d->dy + (sub == 2 ? yn : 0);
+    const int rc = route == 0 ? spyr_wgrad_halo_launch(d, x, dy, partial, sub * per_sub, stream)
+                              : wgrad_tc_launch(d, x, dy, partial, sub * per_sub, stream);
+    if (rc) return rc;
+  }
+  if (partial != nullptr) {
+    const int nimg = d->per_image ? d->B : 1;
+    const int cs = d->cin_stride > 0 ? d->cin_stride : d->Cin;
+    const int rows = cs < d->Cin ? cs : d->Cin;  // operand channels that have a row in dw
+    const long long total = (long long)nimg * d->ksize * d->ksize * rows * (d->Cout / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, slices, nimg, d->dw, d->ksize * d->ksize, rows, cs,
+                                                        d->Cout);
+    spyr_count_launch();
+    SPYR_LAUNCH_CHECK();
+  }
   return 0;
 }

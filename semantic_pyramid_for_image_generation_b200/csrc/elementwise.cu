@@ -13,24 +13,6 @@ extern void spyr_count_launch();
 
 namespace {
 
-__device__ __forceinline__ void ld8(const bf16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16x2(w[j]);
-    v[2 * j] = f.x;
-    v[2 * j + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void st8(bf16* p, const float* v) {
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
 
 inline int grid_for(long long n, int block) {
   long long g = (n + block - 1) / block;
@@ -42,7 +24,7 @@ inline int grid_for(long long n, int block) {
 // 3-channel image <-> 32-wide im2col rows (k = tap*3 + c, taps row-major over (dy,dx), 27..31 zero)
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col3x3_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ mean,
-                                 const float* __restrict__ invstd, bf16* __restrict__ out) {
+                                 const float* __restrict__ invstd, const Act out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)B * H * W;
   if (idx >= npix) return;
@@ -68,12 +50,12 @@ __global__ void im2col3x3_kernel(const float* __restrict__ img, int B, int H, in
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[t * 3 + c] = in ? (__ldg(base + ((size_t)c * H + hh) * W + ww) - m[c]) * is[c] : 0.f;
   }
-  bf16* dst = out + idx * 32;
+  const Act dst = out + idx * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g) st8(dst + g * 8, v + g * 8);
 }
 
-__global__ void col2im3x3_kernel(const bf16* __restrict__ gcol, int B, int H, int W, const float* __restrict__ invstd,
+__global__ void col2im3x3_kernel(const Act gcol, int B, int H, int W, const float* __restrict__ invstd,
                                  float* __restrict__ gimg, int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)B * H * W;
@@ -87,9 +69,9 @@ __global__ void col2im3x3_kernel(const bf16* __restrict__ gcol, int B, int H, in
     // col[p][t] = img[p + d_t]  =>  gimg[q] += gcol[q - d_t][t]
     const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const bf16* src = gcol + (((size_t)b * H + hh) * W + ww) * 32 + t * 3;
+    const Act src = gcol + ((((size_t)b * H + hh) * W + ww) * 32 + t * 3);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) acc[c] += __bfloat162float(src[c]);
+    for (int c = 0; c < 3; ++c) acc[c] += ldf(src, c);
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -101,7 +83,7 @@ __global__ void col2im3x3_kernel(const bf16* __restrict__ gcol, int B, int H, in
 }
 
 // (B,3,H,W) f32 -> 2x2 average -> (B,H/2,W/2,8) bf16 (channels 3..7 zero): input of the D input block's skip conv
-__global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, int H, int W, bf16* __restrict__ out) {
+__global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, int H, int W, const Act out) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW) return;
@@ -116,17 +98,17 @@ __global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, in
   }
   st8(out + idx * 8, v);
 }
-__global__ void img_avgpool_pad8_bwd_kernel(const bf16* __restrict__ g8, int B, int H, int W, float* __restrict__ gimg,
+__global__ void img_avgpool_pad8_bwd_kernel(const Act g8, int B, int H, int W, float* __restrict__ gimg,
                                             int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W) return;
   const int w = (int)(idx % W);
   const int h = (int)((idx / W) % H);
   const int b = (int)(idx / ((long long)W * H));
-  const bf16* src = g8 + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * 8;
+  const Act src = g8 + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * 8;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float v = 0.25f * __bfloat162float(src[c]);
+    const float v = 0.25f * ldf(src, c);
     float* dst = gimg + (((size_t)b * 3 + c) * H + h) * W + w;
     *dst = accumulate ? (*dst + v) : v;
   }
@@ -136,7 +118,7 @@ __global__ void img_avgpool_pad8_bwd_kernel(const bf16* __restrict__ g8, int B, 
 // NCHW f32 <-> NHWC bf16 (API boundary only), optional per-pixel mask gate
 // ---------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ mask, float slope,
-                                    bf16* __restrict__ dst, int C, int HW) {
+                                    const Act dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -150,18 +132,18 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* 
     if (p < HW && c < C) {
       float v = tile[threadIdx.x][i];
       if (mask != nullptr) v *= mask[(size_t)b * HW + p];
-      dst[((size_t)b * HW + p) * C + c] = __float2bfloat16(lrelu_f(v, slope));
+      stf(dst, ((size_t)b * HW + p) * C + c, lrelu_f(v, slope));
     }
   }
 }
-__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, const float* __restrict__ gate_x, float slope,
+__global__ void nhwc_to_nchw_kernel(const Act src, const float* __restrict__ gate_x, float slope,
                                     float* __restrict__ dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[((size_t)b * HW + p) * C + c]) : 0.f;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? ldf(src, ((size_t)b * HW + p) * C + c) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -175,7 +157,7 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, const float* _
   }
 }
 
-__global__ void maskgate_kernel(const bf16* __restrict__ f, const float* __restrict__ mask, bf16* __restrict__ out,
+__global__ void maskgate_kernel(const Act f, const float* __restrict__ mask, const Act out,
                                 long long npix, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix * cg) return;
@@ -191,8 +173,8 @@ __global__ void maskgate_kernel(const bf16* __restrict__ f, const float* __restr
 // ---------------------------------------------------------------------------------------------
 // pooling
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual, bf16* __restrict__ y_raw,
-                                    bf16* __restrict__ y_act, float slope, int B, int H, int W, int cg) {
+__global__ void avgpool2_fwd_kernel(const Act x, const Act residual, const Act y_raw,
+                                    const Act y_act, float slope, int B, int H, int W, int cg) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -203,7 +185,7 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __re
   const int h = (int)(t % OH);
   const int b = (int)(t / OH);
   const size_t C = (size_t)cg * 8;
-  const bf16* p = x + (((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8;
+  const Act p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
   float a[8], v[8];
   ld8(p, v);
   ld8(p + C, a);
@@ -215,20 +197,20 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __re
   ld8(p + (size_t)W * C + C, a);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.25f * (v[j] + a[j]);
-  if (residual != nullptr) {
+  if (!residual.null()) {
     ld8(residual + idx * 8, a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += a[j];
   }
-  if (y_raw != nullptr) st8(y_raw + idx * 8, v);
-  if (y_act != nullptr) {
+  if (!y_raw.null()) st8(y_raw + idx * 8, v);
+  if (!y_act.null()) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = lrelu_f(v[j], slope);
     st8(y_act + idx * 8, v);
   }
 }
 // g_hi[b,h,w,:] = 0.25 * g_lo[b,h/2,w/2,:]   (H, W are the high-resolution dims)
-__global__ void avgpool2_bwd_kernel(const bf16* __restrict__ g_lo, bf16* __restrict__ g_hi, int B, int H, int W, int cg) {
+__global__ void avgpool2_bwd_kernel(const Act g_lo, const Act g_hi, int B, int H, int W, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
   const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
@@ -244,7 +226,7 @@ __global__ void avgpool2_bwd_kernel(const bf16* __restrict__ g_lo, bf16* __restr
   st8(g_hi + idx * 8, v);
 }
 
-__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int cg) {
+__global__ void maxpool2_fwd_kernel(const Act x, const Act y, int B, int H, int W, int cg) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -255,7 +237,7 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
   const int h = (int)(t % OH);
   const int b = (int)(t / OH);
   const size_t C = (size_t)cg * 8;
-  const bf16* p = x + (((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8;
+  const Act p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
   float a[8], v[8];
   ld8(p, v);
   ld8(p + C, a);
@@ -271,7 +253,7 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
 }
 // routes gy to the FIRST maximum of each 2x2 window in (row, col) scan order (ATen max_pool2d backward),
 // optionally gated by x > 0 (the ReLU that produced x).
-__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy, bf16* __restrict__ gx, int B,
+__global__ void maxpool2_bwd_kernel(const Act x, const Act gy, const Act gx, int B,
                                     int H, int W, int cg, int relu_gate, int accumulate) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -325,7 +307,7 @@ __device__ __forceinline__ void adaptive_win(int i, int in, int out, int* s, int
   *s = (i * in) / out;
   *e = ((i + 1) * in + out - 1) / out;
 }
-__global__ void adaptive_avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int OH,
+__global__ void adaptive_avgpool_fwd_kernel(const Act x, const Act y, int B, int H, int W, int OH,
                                             int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -350,8 +332,8 @@ __global__ void adaptive_avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __
   for (int j = 0; j < 8; ++j) acc[j] *= inv;
   st8(y + idx * 8, acc);
 }
-__global__ void adaptive_avgpool_bwd_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ residual,
-                                            bf16* __restrict__ gx, int B, int H, int W, int OH, int OW, int cg) {
+__global__ void adaptive_avgpool_bwd_kernel(const Act gy, const Act residual,
+                                            const Act gx, int B, int H, int W, int OH, int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
   const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
@@ -375,7 +357,7 @@ __global__ void adaptive_avgpool_bwd_kernel(const bf16* __restrict__ gy, const b
       for (int j = 0; j < 8; ++j) acc[j] += a[j] * inv;
     }
   }
-  if (residual != nullptr) {
+  if (!residual.null()) {
     ld8(residual + idx * 8, a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += a[j];
@@ -384,32 +366,32 @@ __global__ void adaptive_avgpool_bwd_kernel(const bf16* __restrict__ gy, const b
 }
 
 // feat[b][c] = mean_p lrelu(x[b,p,c])  (models.py:125-127); one block per image, threads over channels
-__global__ void global_avgpool_lrelu_fwd_kernel(const bf16* __restrict__ x, float slope, float* __restrict__ out, int P,
+__global__ void global_avgpool_lrelu_fwd_kernel(const Act x, float slope, float* __restrict__ out, int P,
                                                 int C) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int p = 0; p < P; ++p) acc += lrelu_f(__bfloat162float(x[((size_t)b * P + p) * C + c]), slope);
+    for (int p = 0; p < P; ++p) acc += lrelu_f(ldf(x, ((size_t)b * P + p) * C + c), slope);
     out[(size_t)b * C + c] = acc / (float)P;
   }
 }
-__global__ void global_avgpool_lrelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gfeat, float slope,
-                                                bf16* __restrict__ gx, int P, int C) {
+__global__ void global_avgpool_lrelu_bwd_kernel(const Act x, const float* __restrict__ gfeat, float slope,
+                                                const Act gx, int P, int C) {
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < P * C; i += blockDim.x) {
     const int c = i % C;
-    const float xv = __bfloat162float(x[(size_t)b * P * C + i]);
+    const float xv = ldf(x, (size_t)b * P * C + i);
     const float g = gfeat[(size_t)b * C + c] / (float)P;
-    gx[(size_t)b * P * C + i] = __float2bfloat16(xv > 0.f ? g : g * slope);
+    stf(gx, (size_t)b * P * C + i, xv > 0.f ? g : g * slope);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // out = gamma * t + x   and its backward  (SelfAttention tail, models.py:274)
 // ---------------------------------------------------------------------------------------------
-__global__ void gamma_residual_fwd_kernel(const bf16* __restrict__ t, const bf16* __restrict__ x,
-                                          const float* __restrict__ gamma, bf16* __restrict__ out,
-                                          bf16* __restrict__ out_act, float slope, long long n8) {
+__global__ void gamma_residual_fwd_kernel(const Act t, const Act x,
+                                          const float* __restrict__ gamma, const Act out,
+                                          const Act out_act, float slope, long long n8) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n8) return;
   const float g = __ldg(gamma);
@@ -419,17 +401,18 @@ __global__ void gamma_residual_fwd_kernel(const bf16* __restrict__ t, const bf16
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = g * a[j] + b[j];
   st8(out + idx * 8, a);
-  if (out_act != nullptr) {
-    // activate the BF16-rounded value the raw output holds
+  if (!out_act.null()) {
+    // activate the value the raw output holds (BF16-rounded, or hi + lo in split mode)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = lrelu_f(__bfloat162float(__float2bfloat16(a[j])), slope);
+    for (int j = 0; j < 8; ++j) a[j] = lrelu_f(stored_value(a[j], out.lo), slope);
     st8(out_act + idx * 8, a);
   }
 }
 // gt = gamma * g ; dgamma += sum(g * t)
-__global__ void gamma_residual_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ t,
-                                          const float* __restrict__ gamma, bf16* __restrict__ gt,
-                                          float* __restrict__ dgamma, long long n8) {
+__global__ void gamma_residual_bwd_kernel(const Act g, const Act t,
+                                          const float* __restrict__ gamma, const Act gt,
+                                          float* __restrict__ dgamma, long long n8, float* __restrict__ scratch,
+                                          unsigned int* ticket) {
   const float gm = __ldg(gamma);
   float acc = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8; idx += (long long)gridDim.x * blockDim.x) {
@@ -450,22 +433,25 @@ __global__ void gamma_residual_bwd_kernel(const bf16* __restrict__ g, const bf16
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(dgamma, v);
+    if (threadIdx.x == 0) scratch[blockIdx.x] = v;
   }
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, 1, [&](int, float total) { *dgamma += total; });
 }
 
 // out_i[c] += sum_rows g[row][c]   (bias gradients; up to three identical destinations)
-__global__ void colsum_kernel(const bf16* __restrict__ g, long long rows, int cg, float* __restrict__ o0,
-                              float* __restrict__ o1, float* __restrict__ o2) {
+__global__ void colsum_kernel(const Act g, long long rows, int cg, float* __restrict__ o0,
+                              float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ scratch,
+                              unsigned int* ticket) {
   extern __shared__ float sh[];  // [prows][cg*8]
   const int c = threadIdx.x % cg;
   const int pr = threadIdx.x / cg;
   const int prows = blockDim.x / cg;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
   if (pr < prows)
-#pragma unroll 4  // four independent 16-byte loads in flight per thread (a rolled loop has one)
+#pragma unroll 8  // eight independent 16-byte loads in flight per thread (a rolled loop has one)
     for (long long r = (long long)blockIdx.x * prows + pr; r < rows; r += (long long)gridDim.x * prows) {
-      ld8(g + (r * cg + c) * 8, a);
+      ld8_nc(g + (r * cg + c) * 8, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += a[j];
     }
@@ -478,16 +464,21 @@ __global__ void colsum_kernel(const bf16* __restrict__ g, long long rows, int cg
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += sh[r * C + i];
-    atomicAdd(o0 + i, s);
-    if (o1 != nullptr) atomicAdd(o1 + i, s);
-    if (o2 != nullptr) atomicAdd(o2 + i, s);
+    scratch[(size_t)blockIdx.x * C + i] = s;
   }
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, C, [&](int i, float total) {
+      o0[i] += total;
+      if (o1 != nullptr) o1[i] += total;
+      if (o2 != nullptr) o2[i] += total;
+    });
 }
 
 // dw[(t*cin_stride + ci_row)*Cout + co] += sum_{b,h,w} mask[b,h+dy,w+dx] * g[b,h,w,co]
 // (weight gradient of the mask channel of `cat(feature*mask, mask)`, models.py:94,336)
-__global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16* __restrict__ g, int B, int H, int W,
-                                     int cg, float* __restrict__ dw, int cin_stride, int ci_row) {
+__global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const Act g, int B, int H, int W,
+                                     int cg, float* __restrict__ dw, int cin_stride, int ci_row,
+                                     float* __restrict__ scratch, unsigned int* ticket) {
   extern __shared__ float sh[];  // [prows][9][C]
   const int C = cg * 8;
   const int c = threadIdx.x % cg;
@@ -542,9 +533,13 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const bf16*
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += sh[r * 9 * C + i];
-    const int t = i / C, co = i % C;
-    if (s != 0.f) atomicAdd(dw + ((size_t)t * cin_stride + ci_row) * C + co, s);
+    scratch[(size_t)blockIdx.x * 9 * C + i] = s;
   }
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, 9 * C, [&](int i, float total) {
+      const int t = i / C, co = i % C;
+      dw[((size_t)t * cin_stride + ci_row) * C + co] += total;
+    });
 }
 
 // dst[t][n][k] = src[taps-1-t][k][n]: the packed forward weights [tap][Cout][Cin] re-laid out as the K-major operand of
@@ -598,7 +593,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
-                                   unsigned long long offset, float* __restrict__ y, bf16* __restrict__ y_bf16,
+                                   unsigned long long offset, float* __restrict__ y, const Act y_bf16,
                                    unsigned char* __restrict__ mask) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -607,7 +602,7 @@ __global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, flo
   const float v = keep ? x[i] / (1.f - p) : 0.f;
   mask[i] = keep ? 1 : 0;
   if (y != nullptr) y[i] = v;
-  if (y_bf16 != nullptr) y_bf16[i] = __float2bfloat16(v);
+  if (!y_bf16.null()) stf(y_bf16, (size_t)i, v);
 }
 __global__ void dropout_bwd_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mask, long long n, float p,
                                    float* __restrict__ out) {
@@ -615,35 +610,37 @@ __global__ void dropout_bwd_kernel(const float* __restrict__ g, const unsigned c
   if (i < n) out[i] = mask[i] ? g[i] / (1.f - p) : 0.f;
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, const Act dst, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < n) dst[idx] = __float2bfloat16(src[idx]);
+  if (idx < n) stf(dst, (size_t)idx, src[idx]);
 }
 
-__global__ void vec_epilogue_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+__global__ void vec_epilogue_kernel(const float* __restrict__ acc, int nsplit, const float* __restrict__ bias,
                                     const float* __restrict__ add, const float* __restrict__ gate, int mode,
-                                    float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int ld_bf16, int B, int N) {
+                                    float* __restrict__ out_f32, const Act out_bf16, int ld_bf16, int B, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * N) return;
   float v = acc[i];
+  for (int sp = 1; sp < nsplit; ++sp) v += acc[(size_t)sp * B * N + i];  // split-K partial sums, fixed order
   if (bias != nullptr) v += bias[i % N];
   if (add != nullptr) v += add[i];
   if (mode == 1) v = fmaxf(v, 0.f);
   if (mode == 2 && !(gate[i] > 0.f)) v = 0.f;
   if (out_f32 != nullptr) out_f32[i] = v;
-  if (out_bf16 != nullptr) out_bf16[(size_t)(i / N) * ld_bf16 + i % N] = __float2bfloat16(v);
+  if (!out_bf16.null()) stf(out_bf16, (size_t)(i / N) * ld_bf16 + i % N, v);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue of a split-K convolution on a small map: the FP32 accumulator (sum over the K splits, red.global.add) gets
+// Epilogue of a split-K convolution on a small map: the FP32 partial accumulators of the K splits (one slice per split,
+// summed here in split order -- no atomics, bit-reproducible) get
 // the same fused tail as the in-kernel epilogue of spyr_conv2d_fprop: biases, mask-channel stencil, gate, residual,
 // raw + activated BF16 outputs.
 // ---------------------------------------------------------------------------------------------
-__global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H, int W, int cg,
+__global__ void conv_epilogue_kernel(const float* __restrict__ acc, int nsplit, int B, int H, int W, int cg,
                                      const float* __restrict__ bias, const float* __restrict__ bias2,
                                      const float* __restrict__ bias3, const float* __restrict__ stencil_mask,
-                                     const float* __restrict__ stencil_w, const bf16* __restrict__ dmask, float dmask_slope,
-                                     const bf16* __restrict__ residual, bf16* __restrict__ y_raw, bf16* __restrict__ y_act,
+                                     const float* __restrict__ stencil_w, const Act dmask, float dmask_slope,
+                                     const Act residual, const Act y_raw, const Act y_act,
                                      int act, float act_slope) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
@@ -654,6 +651,12 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H
   const float4 a0 = *reinterpret_cast<const float4*>(acc + idx * 8);
   const float4 a1 = *reinterpret_cast<const float4*>(acc + idx * 8 + 4);
   v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+  const size_t slice = (size_t)B * H * W * C;
+  for (int sp = 1; sp < nsplit; ++sp) {
+    const float4 b0 = *reinterpret_cast<const float4*>(acc + sp * slice + idx * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(acc + sp * slice + idx * 8 + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = c * 8 + j;
@@ -676,21 +679,21 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H
       }
     }
   }
-  if (dmask != nullptr) {
+  if (!dmask.null()) {
     float d[8];
-    ld8(dmask + idx * 8, d);
+    ld8(dmask.p + idx * 8, d);  // the sign of a value is the sign of its hi part
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (!(d[j] > 0.f)) v[j] *= dmask_slope;
   }
-  if (residual != nullptr) {
+  if (!residual.null()) {
     float r[8];
     ld8(residual + idx * 8, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += r[j];
   }
-  if (y_raw != nullptr) st8(y_raw + idx * 8, v);
-  if (y_act != nullptr) {
+  if (!y_raw.null()) st8(y_raw + idx * 8, v);
+  if (!y_act.null()) {
     const float sl = (act == 1) ? 0.f : ((act == 2) ? act_slope : 1.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
@@ -702,7 +705,7 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int B, int H
 // generator tail: img = tanh(conv1x1(a; W/sigma) + b), C -> 3 channels, NCHW f32 out  (models.py:58-61,99)
 // ---------------------------------------------------------------------------------------------
 template <int CO>
-__global__ void conv1x1_tanh_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+__global__ void conv1x1_tanh_fwd_kernel(const Act a, const float* __restrict__ w,
                                         const float* __restrict__ sigma, const float* __restrict__ bias,
                                         float* __restrict__ img, int HW, int C, long long npix) {
   extern __shared__ float ws[];  // [CO][C]
@@ -729,9 +732,10 @@ __global__ void conv1x1_tanh_fwd_kernel(const bf16* __restrict__ a, const float*
 // gh[p][k] = (sum_o gpre[o] W[o][k]/sigma) * lrelu'(a[p][k]);  dW_sn[o][k] += sum_p gpre[o] a[p][k];  db[o] += sum_p gpre[o]
 template <int CO>
 __global__ void conv1x1_tanh_bwd_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
-                                        const bf16* __restrict__ a, const float* __restrict__ w,
-                                        const float* __restrict__ sigma, float slope, bf16* __restrict__ gh,
-                                        float* __restrict__ dw, float* __restrict__ db, int HW, int C, long long npix) {
+                                        const Act a, const float* __restrict__ w,
+                                        const float* __restrict__ sigma, float slope, const Act gh,
+                                        float* __restrict__ dw, float* __restrict__ db, int HW, int C, long long npix,
+                                        float* __restrict__ scratch, unsigned int* ticket) {
   extern __shared__ float sh[];  // ws[CO][C] then red[prows][CO][C] then redb[prows][CO]
   const int cg = C / 8;
   const int c = threadIdx.x % cg;
@@ -789,13 +793,18 @@ __global__ void conv1x1_tanh_bwd_kernel(const float* __restrict__ gimg, const fl
   for (int i = threadIdx.x; i < CO * C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += red[r * CO * C + i];
-    atomicAdd(dw + i, s);
+    scratch[(size_t)blockIdx.x * (CO * C + CO) + i] = s;
   }
   if (threadIdx.x < CO) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += redb[r * CO + threadIdx.x];
-    atomicAdd(db + threadIdx.x, s);
+    scratch[(size_t)blockIdx.x * (CO * C + CO) + CO * C + threadIdx.x] = s;
   }
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, CO * C + CO, [&](int i, float total) {
+      if (i < CO * C) dw[i] += total;
+      else db[i - CO * C] += total;
+    });
 }
 
 }  // namespace
@@ -806,7 +815,7 @@ extern "C" int spyr_im2col3x3(const float* img, int B, int H, int W, const float
                               void* stream) {
   SPYR_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "im2col3x3: bad arguments");
   const long long n = (long long)B * H * W;
-  im2col3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(img, B, H, W, mean3, invstd3, (bf16*)out);
+  im2col3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(img, B, H, W, mean3, invstd3, make_act(out, n * 32));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -815,7 +824,7 @@ extern "C" int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float
                               void* stream) {
   SPYR_REQUIRE(gcol && gimg && B > 0, "col2im3x3: bad arguments");
   const long long n = (long long)B * H * W;
-  col2im3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)gcol, B, H, W, invstd3, gimg,
+  col2im3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(make_act(gcol, n * 32), B, H, W, invstd3, gimg,
                                                                        accumulate);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -824,7 +833,7 @@ extern "C" int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float
 extern "C" int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void* out, void* stream) {
   SPYR_REQUIRE(img && out && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8: bad arguments");
   const long long n = (long long)B * (H / 2) * (W / 2);
-  img_avgpool_pad8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, (bf16*)out);
+  img_avgpool_pad8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, make_act(out, n * 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -832,7 +841,7 @@ extern "C" int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void
 extern "C" int spyr_img_avgpool_pad8_bwd(const void* g8, int B, int H, int W, float* gimg, int accumulate, void* stream) {
   SPYR_REQUIRE(g8 && gimg && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8_bwd: bad arguments");
   const long long n = (long long)B * H * W;
-  img_avgpool_pad8_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g8, B, H, W, gimg,
+  img_avgpool_pad8_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g8, n * 2), B, H, W, gimg,
                                                                                   accumulate);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -842,7 +851,7 @@ extern "C" int spyr_nchw_to_nhwc(const float* src, const float* mask, float slop
                                  void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, slope, (bf16*)dst, C, HW);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, slope, make_act(dst, (long long)B * C * HW), C, HW);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -851,14 +860,14 @@ extern "C" int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slo
                                  void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, gate_x, slope, dst, C, HW);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(make_act(src, (long long)B * C * HW), gate_x, slope, dst, C, HW);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream) {
   SPYR_C8(C);
-  maskgate_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)f, mask, (bf16*)out, npix,
+  maskgate_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(make_act(f, npix * C), mask, make_act(out, npix * C), npix,
                                                                                    C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -870,8 +879,8 @@ extern "C" int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_ra
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  avgpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)residual,
-                                                                          (bf16*)y_raw, (bf16*)y_act, slope, B, H, W, C / 8);
+  avgpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(residual, n * 8),
+                                                                          make_act(y_raw, n * 8), make_act(y_act, n * 8), slope, B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -880,7 +889,7 @@ extern "C" int spyr_avgpool2_bwd(const void* g_lo, void* g_hi, int B, int H, int
   SPYR_C8(C);
   const long long n = (long long)B * H * W * (C / 8);
   SPYR_N32(n);
-  avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)g_lo, (bf16*)g_hi, B, H, W, C / 8);
+  avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g_lo, n * 2), make_act(g_hi, n * 8), B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -890,7 +899,7 @@ extern "C" int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, in
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  maxpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C / 8);
+  maxpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(y, n * 8), B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -900,7 +909,7 @@ extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B,
   SPYR_C8(C);
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gy, (bf16*)gx, B, H,
+  maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(gy, n * 8), make_act(gx, n * 32), B, H,
                                                                           W, C / 8, relu_gate, accumulate);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -910,7 +919,7 @@ extern "C" int spyr_adaptive_avgpool_fwd(const void* x, void* y, int B, int H, i
   SPYR_C8(C);
   const long long n = (long long)B * OH * OW * (C / 8);
   SPYR_N32(n);
-  adaptive_avgpool_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, OH, OW,
+  adaptive_avgpool_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * H * W * C), make_act(y, n * 8), B, H, W, OH, OW,
                                                                                   C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -922,20 +931,20 @@ extern "C" int spyr_adaptive_avgpool_bwd(const void* gy, const void* residual, v
   const long long n = (long long)B * H * W * (C / 8);
   SPYR_N32(n);
   adaptive_avgpool_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)gy, (const bf16*)residual, (bf16*)gx, B, H, W, OH, OW, C / 8);
+      make_act(gy, (long long)B * OH * OW * C), make_act(residual, n * 8), make_act(gx, n * 8), B, H, W, OH, OW, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_global_avgpool_lrelu_fwd(const void* x, float slope, float* out, int B, int P, int C, void* stream) {
-  global_avgpool_lrelu_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, slope, out, P, C);
+  global_avgpool_lrelu_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), slope, out, P, C);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, float slope, void* gx, int B, int P, int C,
                                              void* stream) {
-  global_avgpool_lrelu_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gfeat, slope, (bf16*)gx, P, C);
+  global_avgpool_lrelu_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), gfeat, slope, make_act(gx, (long long)B * P * C), P, C);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -944,37 +953,42 @@ extern "C" int spyr_gamma_residual_fwd(const void* t, const void* x, const float
                                        float slope, long long n, void* stream) {
   SPYR_REQUIRE(n % 8 == 0, "gamma_residual_fwd: n must be a multiple of 8");
   gamma_residual_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)t, (const bf16*)x, gamma, (bf16*)out, (bf16*)out_act, slope, n / 8);
+      make_act(t, n), make_act(x, n), gamma, make_act(out, n), make_act(out_act, n), slope, n / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_gamma_residual_bwd(const void* g, const void* t, const float* gamma, void* gt, float* dgamma,
-                                       long long n, void* stream) {
+                                       long long n, void* scratch, void* stream) {
   SPYR_REQUIRE(n % 8 == 0, "gamma_residual_bwd: n must be a multiple of 8");
+  SPYR_REQUIRE(scratch != nullptr, "gamma_residual_bwd: scratch is NULL");
   int grid = grid_for(n / 8, 256);
-  if (grid > 592) grid = 592;
-  gamma_residual_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)g, (const bf16*)t, gamma, (bf16*)gt,
-                                                                    dgamma, n / 8);
+  if (grid > SPYR_REDUCE_BLOCKS) grid = SPYR_REDUCE_BLOCKS;
+  gamma_residual_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(g, n), make_act(t, n), gamma, make_act(gt, n),
+                                                                    dgamma, n / 8, (float*)scratch, spyr_next_ticket());
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* stream) {
+extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* scratch,
+                           void* stream) {
+  SPYR_REQUIRE(scratch != nullptr, "colsum: scratch is NULL");
   SPYR_C8(C);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "colsum: C=%d too large", C);
   const int prows = 256 / cg;
   const int threads = prows * cg;
   long long want = (rows + prows * 8 - 1) / (prows * 8);
-  int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
-  colsum_kernel<<<grid, threads, (size_t)prows * C * 4, (cudaStream_t)stream>>>((const bf16*)g, rows, cg, out0, out1, out2);
+  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+  colsum_kernel<<<grid, threads, (size_t)prows * C * 4, (cudaStream_t)stream>>>(make_act(g, rows * C), rows, cg, out0, out1,
+                                                                                out2, (float*)scratch, spyr_next_ticket());
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride,
-                                  int ci_row, void* stream) {
+                                  int ci_row, void* scratch, void* stream) {
+  SPYR_REQUIRE(scratch != nullptr, "stencil_wgrad: scratch is NULL");
   SPYR_C8(C);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 128, "stencil_wgrad: C=%d too large", C);
@@ -989,9 +1003,10 @@ extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H
   }
   const long long npix = (long long)B * H * W;
   long long want = (npix + prows * 16 - 1) / (prows * 16);
-  int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
-  stencil_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mask, (const bf16*)g, B, H, W, cg, dw, cin_stride,
-                                                                      ci_row);
+  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+  stencil_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mask, make_act(g, npix * C), B, H, W, cg, dw,
+                                                                      cin_stride, ci_row, (float*)scratch,
+                                                                      spyr_next_ticket());
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1001,6 +1016,12 @@ extern "C" int spyr_weight_transpose_flip(const void* src, void* dst, int taps, 
   dim3 grid(ceil_div(N, 32), ceil_div(K, 32), taps);
   weight_transpose_flip_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, taps, K, N);
   spyr_count_launch();
+  if (spyr_split()) {  // the lo plane of the pack follows its hi plane
+    const size_t n = (size_t)taps * K * N;
+    weight_transpose_flip_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)src + n, (bf16*)dst + n, taps,
+                                                                                 K, N);
+    spyr_count_launch();
+  }
   SPYR_LAUNCH_CHECK();
   return 0;
 }
@@ -1016,7 +1037,7 @@ extern "C" int spyr_wgrad_to_oihw(const float* gw, float* out, int taps, int Cin
 extern "C" int spyr_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset,
                                 float* y, void* y_bf16, unsigned char* mask, void* stream) {
   SPYR_REQUIRE(x && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments (0 <= p < 1)");
-  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, (bf16*)y_bf16, mask);
+  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, make_act(y_bf16, n), mask);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1029,16 +1050,17 @@ extern "C" int spyr_dropout_bwd(const float* g, const unsigned char* mask, long 
   return 0;
 }
 extern "C" int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
-  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, make_act(dst, n), n);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_vec_epilogue(const float* acc, const float* bias, const float* add, const float* gate, int mode,
-                                 float* out_f32, void* out_bf16, int ld_bf16, int B, int N, void* stream) {
-  SPYR_REQUIRE(acc && (mode != 2 || gate) && (out_bf16 == nullptr || ld_bf16 >= N), "vec_epilogue: bad arguments");
+extern "C" int spyr_vec_epilogue(const float* acc, int nsplit, const float* bias, const float* add, const float* gate,
+                                 int mode, float* out_f32, void* out_bf16, int ld_bf16, int B, int N, void* stream) {
+  SPYR_REQUIRE(acc && nsplit >= 1 && (mode != 2 || gate) && (out_bf16 == nullptr || ld_bf16 >= N),
+               "vec_epilogue: bad arguments");
   vec_epilogue_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, bias, add, gate, mode, out_f32, (bf16*)out_bf16, ld_bf16, B, N);
+      acc, nsplit, bias, add, gate, mode, out_f32, make_act(out_bf16, (long long)B * ld_bf16), ld_bf16, B, N);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1048,9 +1070,9 @@ extern "C" int spyr_conv2d_epilogue(const spyr_conv_desc* d, const float* acc, v
   SPYR_C8(d->Cout);
   const long long n = (long long)d->B * d->H * d->W * (d->Cout / 8);
   conv_epilogue_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, d->B, d->H, d->W, d->Cout / 8, d->bias, d->bias2, d->bias3, d->stencil_mask, d->stencil_w,
-      (const bf16*)d->dmask, d->dmask_slope, (const bf16*)d->residual, (bf16*)d->y_raw, (bf16*)d->y_act, d->act,
-      d->act_slope);
+      acc, d->splits < 1 ? 1 : d->splits, d->B, d->H, d->W, d->Cout / 8, d->bias, d->bias2, d->bias3, d->stencil_mask,
+      d->stencil_w, make_act(d->dmask, n * 8), d->dmask_slope, make_act(d->residual, n * 8), make_act(d->y_raw, n * 8),
+      make_act(d->y_act, n * 8), d->act, d->act_slope);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1062,10 +1084,10 @@ extern "C" int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float*
   const long long npix = (long long)B * HW;
   const size_t smem = (size_t)Cout * C * 4;
   if (Cout == 3)
-    conv1x1_tanh_fwd_kernel<3><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>((const bf16*)a, w, sigma, bias, img,
+    conv1x1_tanh_fwd_kernel<3><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
                                                                                          HW, C, npix);
   else
-    conv1x1_tanh_fwd_kernel<1><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>((const bf16*)a, w, sigma, bias, img,
+    conv1x1_tanh_fwd_kernel<1><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
                                                                                          HW, C, npix);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
@@ -1073,7 +1095,8 @@ extern "C" int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float*
 }
 extern "C" int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, const float* w, const float* sigma,
                                      float slope, void* gh, float* dw, float* db, int B, int HW, int C, int Cout,
-                                     void* stream) {
+                                     void* scratch, void* stream) {
+  SPYR_REQUIRE(scratch != nullptr, "conv1x1_tanh_bwd: scratch is NULL");
   SPYR_C8(C);
   SPYR_REQUIRE(Cout == 3 || Cout == 1, "conv1x1_tanh_bwd: out_channels must be 1 or 3 (got %d)", Cout);
   const int cg = C / 8;
@@ -1084,13 +1107,16 @@ extern "C" int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const 
   const size_t smem = ((size_t)Cout * C + (size_t)prows * Cout * C + (size_t)prows * Cout) * 4;
   SPYR_REQUIRE(smem <= 48 * 1024, "conv1x1_tanh_bwd: smem %zu too large", smem);
   long long want = (npix + prows * 16 - 1) / (prows * 16);
-  int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+  unsigned int* ticket = spyr_next_ticket();
   if (Cout == 3)
-    conv1x1_tanh_bwd_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, (const bf16*)a, w, sigma, slope,
-                                                                              (bf16*)gh, dw, db, HW, C, npix);
+    conv1x1_tanh_bwd_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
+                                                                              make_act(gh, npix * C), dw, db, HW, C, npix,
+                                                                              (float*)scratch, ticket);
   else
-    conv1x1_tanh_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, (const bf16*)a, w, sigma, slope,
-                                                                              (bf16*)gh, dw, db, HW, C, npix);
+    conv1x1_tanh_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
+                                                                              make_act(gh, npix * C), dw, db, HW, C, npix,
+                                                                              (float*)scratch, ticket);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

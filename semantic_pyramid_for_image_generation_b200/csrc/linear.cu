@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) linear_bwd_w_kernel(const float* __restri
   if (blockIdx.x == 0 && gb != nullptr && threadIdx.x < WROWS && o0 + threadIdx.x < O) {
     float sum = 0.f;
     for (int b = 0; b < B; ++b) sum += gs[threadIdx.x][b];
-    atomicAdd(gb + o0 + threadIdx.x, sum);
+    gb[o0 + threadIdx.x] += sum;  // one thread of one CTA owns this output: plain read-modify-write
   }
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -200,15 +200,30 @@ __global__ void dhead_out_bwd_kernel(const float* __restrict__ g, const float* _
   const int r = blockIdx.x;
   float cls_acc = 0.f;
   for (int k = threadIdx.x; k < E; k += blockDim.x) {
-    float gf = 0.f, ge = 0.f;
+    float gf = 0.f;
     for (int q = 0; q < B; ++q) {
       const float gj = g[((size_t)q * B + r) * E + k];  // i = q, j = r
       gf += gj * emb_w[(size_t)idx[q] * E + k] * inv;
       cls_acc += gj;
-      ge += g[((size_t)r * B + q) * E + k] * feat[(size_t)q * E + k];  // i = r, j = q
     }
     g_feat[(size_t)r * E + k] = gf;
-    if (g_embw != nullptr) atomicAdd(g_embw + (size_t)idx[r] * E + k, ge);
+  }
+  if (g_embw != nullptr) {
+    // samples of the same class share an embedding row: the CTA of the FIRST such sample adds all of them, in batch
+    // order (no atomics, bit-reproducible)
+    const int cls_r = idx[r];
+    bool first = true;
+    for (int q = 0; q < r; ++q) first = first && (idx[q] != cls_r);
+    if (first) {
+      for (int k = threadIdx.x; k < E; k += blockDim.x) {
+        float ge = 0.f;
+        for (int r2 = r; r2 < B; ++r2) {
+          if (idx[r2] != cls_r) continue;
+          for (int q = 0; q < B; ++q) ge += g[((size_t)r2 * B + q) * E + k] * feat[(size_t)q * E + k];  // i = r2, j = q
+        }
+        g_embw[(size_t)cls_r * E + k] += ge;
+      }
+    }
   }
   cls_acc = warp_sum(cls_acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cls_acc;

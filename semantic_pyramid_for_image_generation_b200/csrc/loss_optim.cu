@@ -10,24 +10,6 @@ extern void spyr_count_launch();
 
 namespace {
 
-__device__ __forceinline__ void ld8(const bf16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16x2(w[j]);
-    v[2 * j] = f.x;
-    v[2 * j + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void st8(bf16* p, const float* v) {
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -45,7 +27,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---- attention softmax: one warp per query row ----
-__global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, bf16* __restrict__ p, long long rows, int n) {
+__global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, const Act p, long long rows, int n) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -57,20 +39,20 @@ __global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, bf16* __res
   for (int j = lane; j < n; j += 32) sum += __expf(sr[j] - m);
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int j = lane; j < n; j += 32) p[row * n + j] = __float2bfloat16(__expf(sr[j] - m) * inv);
+  for (int j = lane; j < n; j += 32) stf(p, (size_t)(row * n + j), __expf(sr[j] - m) * inv);
 }
 // dS = P * (dP - sum_k dP*P)
-__global__ void softmax_rows_bwd_kernel(const bf16* __restrict__ p, const float* __restrict__ dp, bf16* __restrict__ ds,
+__global__ void softmax_rows_bwd_kernel(const Act p, const float* __restrict__ dp, const Act ds,
                                         long long rows, int n) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   float d = 0.f;
-  for (int j = lane; j < n; j += 32) d += __bfloat162float(p[row * n + j]) * dp[row * n + j];
+  for (int j = lane; j < n; j += 32) d += ldf(p, (size_t)(row * n + j)) * dp[row * n + j];
   d = warp_sum(d);
   for (int j = lane; j < n; j += 32) {
-    const float pv = __bfloat162float(p[row * n + j]);
-    ds[row * n + j] = __float2bfloat16(pv * (dp[row * n + j] - d));
+    const float pv = ldf(p, (size_t)(row * n + j));
+    stf(ds, (size_t)(row * n + j), pv * (dp[row * n + j] - d));
   }
 }
 
@@ -92,15 +74,15 @@ __global__ void lsgan_bwd_kernel(const float* __restrict__ p, long long n, float
 }
 
 // ---- semantic reconstruction, one pyramid level: loss += mean(|maxpool2(fr) - maxpool2(ff)| * maxpool2(mask)) ----
-__device__ __forceinline__ void pool4(const bf16* x, size_t off, size_t C, size_t WC, float v[4][8]) {
+__device__ __forceinline__ void pool4(const Act& x, size_t off, size_t C, size_t WC, float v[4][8]) {
   ld8(x + off, v[0]);
   ld8(x + off + C, v[1]);
   ld8(x + off + WC, v[2]);
   ld8(x + off + WC + C, v[3]);
 }
-__global__ void rec_level_fwd_kernel(const bf16* __restrict__ fr, const bf16* __restrict__ ff,
+__global__ void rec_level_fwd_kernel(const Act fr, const Act ff,
                                      const float* __restrict__ mask, int B, int H, int W, int cg, float inv_numel,
-                                     float* __restrict__ loss) {
+                                     float* __restrict__ loss, float* __restrict__ scratch, unsigned int* ticket) {
   __shared__ float red[32];
   const int OH = H / 2, OW = W / 2;
   const size_t C = (size_t)cg * 8;
@@ -128,12 +110,14 @@ __global__ void rec_level_fwd_kernel(const bf16* __restrict__ fr, const bf16* __
     }
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(loss, acc * inv_numel);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, 1, [&](int, float total) { *loss += total * inv_numel; });
 }
 // g_ff = d loss / d ff : -sign((pr - pf) * pm) * pm / numel * gout, routed to the first maximum of the 2x2 window
-__global__ void rec_level_bwd_kernel(const bf16* __restrict__ fr, const bf16* __restrict__ ff,
+__global__ void rec_level_bwd_kernel(const Act fr, const Act ff,
                                      const float* __restrict__ mask, int B, int H, int W, int cg, float inv_numel,
-                                     const float* __restrict__ gout, bf16* __restrict__ gff) {
+                                     const float* __restrict__ gout, const Act gff) {
   const int OH = H / 2, OW = W / 2;
   const size_t C = (size_t)cg * 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,7 +167,8 @@ __global__ void rec_level_bwd_kernel(const bf16* __restrict__ fr, const bf16* __
 }
 // vector levels (fc7, logits): MaxPool1d(2) over consecutive pairs, FP32 (B, N)
 __global__ void rec_vec_fwd_kernel(const float* __restrict__ fr, const float* __restrict__ ff,
-                                   const float* __restrict__ mask, int B, int N, float inv_numel, float* __restrict__ loss) {
+                                   const float* __restrict__ mask, int B, int N, float inv_numel, float* __restrict__ loss,
+                                   float* __restrict__ scratch, unsigned int* ticket) {
   __shared__ float red[32];
   const int P = N / 2;
   float acc = 0.f;
@@ -194,7 +179,9 @@ __global__ void rec_vec_fwd_kernel(const float* __restrict__ fr, const float* __
     acc += fabsf((fmaxf(fr[o], fr[o + 1]) - fmaxf(ff[o], ff[o + 1])) * pm);
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(loss, acc * inv_numel);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, 1, [&](int, float total) { *loss += total * inv_numel; });
 }
 __global__ void rec_vec_bwd_kernel(const float* __restrict__ fr, const float* __restrict__ ff,
                                    const float* __restrict__ mask, int B, int N, float inv_numel,
@@ -219,13 +206,15 @@ __global__ void rec_vec_bwd_kernel(const float* __restrict__ fr, const float* __
 
 // ---- diversity: work[0] = mean|z_a - z_b|, work[1] = mean|img_a - img_b|; loss = work[0] / (work[1] + 1e-8) ----
 __global__ void absdiff_mean_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, float* __restrict__ scratch, unsigned int* ticket) {
   __shared__ float red[32];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += fabsf(a[i] - b[i]);
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc * inv_n);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = acc;
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<float>(scratch, (int)gridDim.x, 1, [&](int, float total) { *out = total * inv_n; });
 }
 __global__ void diversity_finalize_kernel(const float* __restrict__ work, float* __restrict__ loss) {
   *loss = work[0] / (work[1] + 1e-08f);
@@ -295,13 +284,13 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 }  // namespace
 
 extern "C" int spyr_softmax_rows_fwd(const float* s, void* p, long long rows, int n, void* stream) {
-  softmax_rows_fwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, (bf16*)p, rows, n);
+  softmax_rows_fwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, make_act(p, rows * n), rows, n);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_softmax_rows_bwd(const void* p, const float* dp, void* ds, long long rows, int n, void* stream) {
-  softmax_rows_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)p, dp, (bf16*)ds, rows, n);
+  softmax_rows_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(make_act(p, rows * n), dp, make_act(ds, rows * n), rows, n);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -319,15 +308,16 @@ extern "C" int spyr_lsgan_bwd(const float* p, long long n, float target, const f
   return 0;
 }
 extern "C" int spyr_rec_level_fwd(const void* fr, const void* ff, const float* mask, int B, int H, int W, int C, float* loss,
-                                  void* stream) {
+                                  void* scratch, void* stream) {
+  SPYR_REQUIRE(scratch != nullptr, "rec_level_fwd: scratch is NULL");
   SPYR_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "rec_level_fwd: bad shape");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
   long long want = (n + 1023) / 1024;
-  const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
-  rec_level_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)fr, (const bf16*)ff, mask, B, H, W, C / 8, inv,
-                                                              loss);
+  const int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+  rec_level_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B, H, W,
+                                                              C / 8, inv, loss, (float*)scratch, spyr_next_ticket());
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -338,16 +328,17 @@ extern "C" int spyr_rec_level_bwd(const void* fr, const void* ff, const float* m
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
-  rec_level_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)fr, (const bf16*)ff, mask, B,
-                                                                                 H, W, C / 8, inv, gout, (bf16*)gff);
+  rec_level_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B,
+                                                                                 H, W, C / 8, inv, gout, make_act(gff, n * 32));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_rec_vec_fwd(const float* fr, const float* ff, const float* mask, int B, int N, float* loss,
-                                void* stream) {
+                                void* scratch, void* stream) {
+  SPYR_REQUIRE(scratch != nullptr, "rec_vec_fwd: scratch is NULL");
   const float inv = 1.f / ((float)B * (float)(N / 2));
-  rec_vec_fwd_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(fr, ff, mask, B, N, inv, loss);
+  rec_vec_fwd_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(fr, ff, mask, B, N, inv, loss, (float*)scratch, spyr_next_ticket());
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -362,15 +353,17 @@ extern "C" int spyr_rec_vec_bwd(const float* fr, const float* ff, const float* m
   return 0;
 }
 extern "C" int spyr_diversity_fwd(const float* img, long long img_half, const float* z, long long z_half, float* work,
-                                  float* loss, void* stream_) {
+                                  float* loss, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(img_half > 0 && z_half > 0, "diversity_fwd: batch must be > 1 (lossfunction.py:100)");
-  SPYR_CHECK_CUDA(cudaMemsetAsync(work, 0, 2 * sizeof(float), stream));
-  absdiff_mean_kernel<<<4, 256, 0, stream>>>(z, z + z_half, z_half, 1.f / (float)z_half, work);
+  SPYR_REQUIRE(scratch != nullptr, "diversity_fwd: scratch is NULL");
+  float* sc = (float*)scratch;
+  absdiff_mean_kernel<<<4, 256, 0, stream>>>(z, z + z_half, z_half, 1.f / (float)z_half, work, sc, spyr_next_ticket());
   spyr_count_launch();
   long long want = (img_half + 2047) / 2048;
-  const int grid = (int)(want < 1 ? 1 : (want > 592 ? 592 : want));
-  absdiff_mean_kernel<<<grid, 256, 0, stream>>>(img, img + img_half, img_half, 1.f / (float)img_half, work + 1);
+  const int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+  absdiff_mean_kernel<<<grid, 256, 0, stream>>>(img, img + img_half, img_half, 1.f / (float)img_half, work + 1,
+                                                sc + SPYR_REDUCE_BLOCKS, spyr_next_ticket());
   spyr_count_launch();
   diversity_finalize_kernel<<<1, 1, 0, stream>>>(work, loss);
   spyr_count_launch();

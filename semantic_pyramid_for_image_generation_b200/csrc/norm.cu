@@ -15,24 +15,6 @@ extern void spyr_count_launch();
 
 namespace {
 
-__device__ __forceinline__ void ld8(const bf16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16x2(w[j]);
-    v[2 * j] = f.x;
-    v[2 * j + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void st8(bf16* p, const float* v) {
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
 
 // p -> (p / d, p % d); every map width here is a power of two, which turns the division into a shift
 __device__ __forceinline__ int pow2_shift(int d) { return (d & (d - 1)) == 0 ? __ffs(d) - 1 : -1; }
@@ -102,7 +84,7 @@ __device__ __forceinline__ void build_gather_tables(Gather* tab, int H, int W, f
   __syncthreads();
 }
 
-__device__ __forceinline__ void up2_load(const bf16* x, int b, int oh, int ow, int H, int W, int cg, int c, float sh,
+__device__ __forceinline__ void up2_load(const Act& x, int b, int oh, int ow, int H, int W, int cg, int c, float sh,
                                          float sw, float* v) {
   const Lerp Lh = lerp_src(oh, H, sh), Lw = lerp_src(ow, W, sw);
   float a[8], bq[8], cq[8], d[8];
@@ -121,8 +103,8 @@ __device__ __forceinline__ void up2_load(const bf16* x, int b, int oh, int ow, i
 // The kernels below are templated on their mode: one body per mode keeps the plain same-resolution cases at ~40
 // registers (full occupancy) instead of inheriting the register count of the interpolating variants.
 template <int up2>
-__global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W, int cg, bf16* __restrict__ xu_out,
-                                double* __restrict__ sums) {
+__global__ void bn_stats_kernel(const Act x, int B, int H, int W, int cg, const Act xu_out,
+                                double* __restrict__ sums, double* __restrict__ scratch, unsigned int* ticket) {
   extern __shared__ float sh[];  // [prows][2][C]
   const int C = cg * 8;
   const int c = threadIdx.x % cg;
@@ -144,10 +126,10 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
         divmod((int)p, OW, sh_w, rowi, ow);
         divmod(rowi, OH, sh_h, b, oh);
         up2_load(x, b, oh, ow, H, W, cg, c, shs, sws, v);
-        if (xu_out != nullptr) {
-          // materialise up2(x) once; the statistics are those of the stored (BF16) values the later passes read
+        if (!xu_out.null()) {
+          // materialise up2(x) once; the statistics are those of the stored values the later passes read
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
+          for (int j = 0; j < 8; ++j) v[j] = stored_value(v[j], xu_out.lo);
           st8(xu_out + (p * cg + c) * 8, v);
         }
       } else {
@@ -171,8 +153,10 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, int B, int H, int W,
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < prows; ++r) s += (double)sh[r * 2 * C + i];
-    atomicAdd(sums + i, s);
+    scratch[(size_t)blockIdx.x * 2 * C + i] = s;
   }
+  if (spyr_last_block(ticket, gridDim.x))
+    spyr_sum_partials<double>(scratch, (int)gridDim.x, 2 * C, [&](int i, double total) { sums[i] = total; });
 }
 
 // mean/rstd from the sums (train) or from the running buffers (eval); running-stat update as nn.BatchNorm2d
@@ -209,10 +193,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // registers and walks over output pixels, so the per-element work is one 16-byte load (four for the bilinear modes)
 // and one or two 16-byte stores.
 template <int mode>
-__global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ mean_rstd,
+__global__ void bn_act_kernel(const Act x, const float* __restrict__ mean_rstd,
                               const float* __restrict__ scale_ptr, const float* __restrict__ shift_ptr, int row_stride,
-                              const int* __restrict__ cls, float slope, bf16* __restrict__ out_a,
-                              bf16* __restrict__ out_xu, int H, int W, int cg) {
+                              const int* __restrict__ cls, float slope, const Act out_a,
+                              const Act out_xu, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = mode ? 2 * H : H, OW = mode ? 2 * W : W;
   const int b = blockIdx.y;
@@ -254,7 +238,7 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
     ld8(x + ((in_base + (size_t)Lh.i1 * W + Lw.i0) * cg + c) * 8, q[2]);
     ld8(x + ((in_base + (size_t)Lh.i1 * W + Lw.i1) * cg + c) * 8, q[3]);
     const float w00 = Lh.w0 * Lw.w0, w01 = Lh.w0 * Lw.w1, w10 = Lh.w1 * Lw.w0, w11 = Lh.w1 * Lw.w1;
-    if (out_xu != nullptr) {
+    if (!out_xu.null()) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = Lh.w0 * (Lw.w0 * q[0][j] + Lw.w1 * q[1][j]) + Lh.w1 * (Lw.w0 * q[2][j] + Lw.w1 * q[3][j]);
       st8(out_xu + o, v);
@@ -286,10 +270,11 @@ __global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restric
 //   mode 3: g is d/dy at 2H x 2W and the normalised tensor is up2(x) (final block): reduce at 2H x 2W
 // ---------------------------------------------------------------------------------------------
 template <int mode>
-__global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
+__global__ void bn_bwd_reduce_kernel(const Act g, const Act x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                      const float* __restrict__ shift_ptr, int row_stride, const int* __restrict__ cls,
-                                     float slope, bf16* __restrict__ gy_out, float* __restrict__ S, int H, int W, int cg) {
+                                     float slope, const Act gy_out, float* __restrict__ S, int H, int W, int cg,
+                                     float* __restrict__ scratch, unsigned int* ticket) {
   extern __shared__ float sh[];  // [prows][2][C]
   __shared__ Gather gtab[GATHER_MAX];
   const int C = cg * 8;
@@ -340,20 +325,15 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
         if (Gh.n <= GATHER_TAPS && Gw.n <= GATHER_TAPS) {
 #pragma unroll
           for (int a = 0; a < GATHER_TAPS; ++a) {
-            uint4 raw[GATHER_TAPS];
+            float raw[GATHER_TAPS][8];
 #pragma unroll
             for (int e = 0; e < GATHER_TAPS; ++e)
-              raw[e] = __ldg(reinterpret_cast<const uint4*>(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8));
+              ld8_nc(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, raw[e]);
 #pragma unroll
             for (int e = 0; e < GATHER_TAPS; ++e) {
               const float wt = Gh.w[a] * Gw.w[e];
-              const uint32_t wv[4] = {raw[e].x, raw[e].y, raw[e].z, raw[e].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(wv[j]);
-                gy[2 * j] += wt * f.x;
-                gy[2 * j + 1] += wt * f.y;
-              }
+              for (int j = 0; j < 8; ++j) gy[j] += wt * raw[e][j];
             }
           }
         } else {
@@ -373,9 +353,9 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
             if (!(y > 0.f)) gy[j] *= slope;
           }
         }
-        // the reduction uses the BF16-rounded value that pass 2 will read back
+        // the reduction uses the stored value that pass 2 will read back
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gy[j] = __bfloat162float(__float2bfloat16(gy[j]));
+        for (int j = 0; j < 8; ++j) gy[j] = stored_value(gy[j], gy_out.lo);
         st8(gy_out + off, gy);
       }
 #pragma unroll
@@ -395,7 +375,12 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __r
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += sh[r * 2 * C + i];
-    atomicAdd(S + (size_t)b * 2 * C + i, s);
+    scratch[((size_t)b * gridDim.x + blockIdx.x) * 2 * C + i] = s;
+  }
+  if (spyr_last_block(ticket, gridDim.x * gridDim.y)) {
+    for (int bb = 0; bb < (int)gridDim.y; ++bb)
+      spyr_sum_partials<float>(scratch + (size_t)bb * gridDim.x * 2 * C, (int)gridDim.x, 2 * C,
+                               [&](int i, float total) { S[(size_t)bb * 2 * C + i] = total; });
   }
 }
 
@@ -414,8 +399,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
     m1 += sc * a1;
     m2 += sc * a2;
     if (d_scale != nullptr) {
-      atomicAdd(d_scale + (size_t)row * row_stride + c, a2);
-      atomicAdd(d_shift + (size_t)row * row_stride + c, a1);
+      // one thread owns channel c of every row and visits the samples in order: plain read-modify-write, fixed order
+      d_scale[(size_t)row * row_stride + c] += a2;
+      d_shift[(size_t)row * row_stride + c] += a1;
     }
   }
   M[c] = m1 / count;
@@ -425,10 +411,10 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
 // pass 2: gx = rstd * (scale * gy - M1 - xhat * M2) (+ residual).  x_up2: gy/gx live at 2H x 2W and xhat is taken
 // from up2(x) (final block, where the statistics are those of the upsampled tensor)
 template <int x_up2>
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ x,
+__global__ void bn_bwd_apply_kernel(const Act gy, const Act x,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                     int row_stride, const int* __restrict__ cls, const float* __restrict__ M,
-                                    const bf16* __restrict__ residual, bf16* __restrict__ gx, int H, int W, int cg) {
+                                    const Act residual, const Act gx, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = x_up2 ? 2 * H : H, OW = x_up2 ? 2 * W : W;
   const int b = blockIdx.y;
@@ -468,7 +454,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __r
       const float xh = (xv[j] - mu[j]) * rs[j];
       o[j] = rs[j] * (sc[j] * g[j] - m1[j] - xh * m2[j]);
     }
-    if (residual != nullptr) {
+    if (!residual.null()) {
       float rv[8];
       ld8(residual + off, rv);
 #pragma unroll
@@ -479,7 +465,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ gy, const bf16* __r
 }
 
 // plain transposed bilinear x2 (align_corners=True): g_lo = up2^T(g_hi)  (skip path of the generator block)
-__global__ void up2_bwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ out, int B, int H, int W, int cg) {
+__global__ void up2_bwd_kernel(const Act g, const Act out, int B, int H, int W, int cg) {
   __shared__ Gather gtab[GATHER_MAX];
   build_gather_tables(gtab, H, W, (float)(H - 1) / (float)(2 * H - 1), (float)(W - 1) / (float)(2 * W - 1));
   const long long n = (long long)B * H * W * cg;
@@ -496,20 +482,15 @@ __global__ void up2_bwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ ou
     if (Gh.n <= GATHER_TAPS && Gw.n <= GATHER_TAPS) {
 #pragma unroll
       for (int a = 0; a < GATHER_TAPS; ++a) {
-        uint4 raw[GATHER_TAPS];
+        float raw[GATHER_TAPS][8];
 #pragma unroll
         for (int e = 0; e < GATHER_TAPS; ++e)
-          raw[e] = __ldg(reinterpret_cast<const uint4*>(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8));
+          ld8_nc(g + ((((size_t)b * 2 * H + Gh.o[a]) * 2 * W + Gw.o[e]) * cg + c) * 8, raw[e]);
 #pragma unroll
         for (int e = 0; e < GATHER_TAPS; ++e) {
           const float wt = Gh.w[a] * Gw.w[e];
-          const uint32_t wv[4] = {raw[e].x, raw[e].y, raw[e].z, raw[e].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16x2(wv[j]);
-            acc[2 * j] += wt * f.x;
-            acc[2 * j + 1] += wt * f.y;
-          }
+          for (int j = 0; j < 8; ++j) acc[j] += wt * raw[e][j];
         }
       }
     } else {
@@ -559,29 +540,38 @@ inline Threads pick_threads(int cg, int max_threads) {
 
 #define SPYR_C8(C) SPYR_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channel count %d must be a multiple of 8", __func__, (int)(C))
 
-static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* stream_);
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* scratch,
+                           void* stream_);
 
-extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* stream) {
-  return bn_stats_launch(x, B, H, W, C, up2, nullptr, sums, stream);
+extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* scratch, void* stream) {
+  return bn_stats_launch(x, B, H, W, C, up2, nullptr, sums, scratch, stream);
 }
-extern "C" int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums, void* stream) {
+extern "C" int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums, void* scratch,
+                              void* stream) {
   SPYR_REQUIRE(xu_out != nullptr, "up2_stats: xu_out is NULL");
-  return bn_stats_launch(x, B, H, W, C, 1, xu_out, sums, stream);
+  return bn_stats_launch(x, B, H, W, C, 1, xu_out, sums, scratch, stream);
 }
-static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* stream_) {
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* scratch,
+                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_C8(C);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "bn_stats: C=%d too large", C);
-  if (sums != nullptr) SPYR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  SPYR_REQUIRE(sums == nullptr || scratch != nullptr, "bn_stats: scratch is NULL");
   const Threads t = pick_threads(cg, 256);
   const long long npix = (long long)B * H * W * (up2 ? 4 : 1);
   long long want = (npix + t.prows * 16 - 1) / (t.prows * 16);
-  const int grid = (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  // without statistics (plain materialisation of up2(x)) nothing is reduced: the grid is not bounded by the scratch
+  const int cap = sums != nullptr ? SPYR_REDUCE_BLOCKS : 1184;
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  const Act xa = make_act(x, (long long)B * H * W * C), xu = make_act(xu_out, npix * C);
+  unsigned int* ticket = spyr_next_ticket();
   if (up2)
-    bn_stats_kernel<1><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, (bf16*)xu_out, sums);
+    bn_stats_kernel<1><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, sums, (double*)scratch,
+                                                                                ticket);
   else
-    bn_stats_kernel<0><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>((const bf16*)x, B, H, W, cg, (bf16*)xu_out, sums);
+    bn_stats_kernel<0><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, sums, (double*)scratch,
+                                                                                ticket);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -611,10 +601,11 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
   const int cap = (2368 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
+  const long long nin = (long long)B * H * W * C, nout = (long long)B * npix * C;
 #define SPYR_BN_ACT(M)                                                                                                  \
-  bn_act_kernel<M><<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, mean_rstd, scale_ptr, shift_ptr, \
-                                                                        row_stride, cls, slope, (bf16*)out_a,          \
-                                                                        (bf16*)out_xu, H, W, cg)
+  bn_act_kernel<M><<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>(make_act(x, nin), mean_rstd, scale_ptr, shift_ptr, \
+                                                                        row_stride, cls, slope, make_act(out_a, nout),   \
+                                                                        make_act(out_xu, nout), H, W, cg)
   if (mode == 0) SPYR_BN_ACT(0);
   else if (mode == 1) SPYR_BN_ACT(1);
   else SPYR_BN_ACT(2);
@@ -625,7 +616,7 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
 }
 extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr,
                                   const float* shift_ptr, int row_stride, const int* cls, float slope, int mode,
-                                  void* gy_out, float* S, int B, int H, int W, int C, void* stream_) {
+                                  void* gy_out, float* S, int B, int H, int W, int C, void* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_C8(C);
   SPYR_REQUIRE(mode == 0 || mode == 3 || gy_out != nullptr, "bn_bwd_reduce: modes 1/2 need gy_out");
@@ -633,17 +624,22 @@ extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mea
   SPYR_REQUIRE((mode != 1 && mode != 2) || H + W <= GATHER_MAX, "bn_bwd_reduce: H + W = %d exceeds the gather table", H + W);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "bn_bwd_reduce: C=%d too large", C);
-  SPYR_CHECK_CUDA(cudaMemsetAsync(S, 0, sizeof(float) * 2 * C * B, stream));
+  SPYR_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch is NULL");
   const Threads t = pick_threads(cg, 256);
   const int npix = H * W * (mode == 3 ? 4 : 1);
   int gx = (npix + t.prows * 8 - 1) / (t.prows * 8);
-  const int cap = (1184 + B - 1) / B;
+  const int cap = SPYR_REDUCE_BLOCKS / B;  // gx * B partial vectors of 2C floats must fit the scratch
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
+  SPYR_REQUIRE(gx * B <= SPYR_REDUCE_BLOCKS, "bn_bwd_reduce: batch %d exceeds %d", B, SPYR_REDUCE_BLOCKS);
   dim3 grid(gx, B);
+  // H, W are x's dims; g lives at 2H x 2W in modes 1, 2 and 3, gy_out (modes 1, 2) at H x W
+  const long long nx = (long long)B * H * W * C, ng = (mode == 1 || mode == 2) ? 4 * nx : (mode == 3 ? 4 * nx : nx);
+  unsigned int* ticket = spyr_next_ticket();
 #define SPYR_BN_RED(M)                                                                  \
   bn_bwd_reduce_kernel<M><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(     \
-      (const bf16*)g, (const bf16*)x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, (bf16*)gy_out, S, H, W, cg)
+      make_act(g, ng), make_act(x, nx), mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, make_act(gy_out, nx), S, \
+      H, W, cg, (float*)scratch, ticket)
   if (mode == 0) SPYR_BN_RED(0);
   else if (mode == 1) SPYR_BN_RED(1);
   else if (mode == 2) SPYR_BN_RED(2);
@@ -673,12 +669,15 @@ extern "C" int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mea
   const int cap = (2368 + B - 1) / B;
   if (gxx > cap) gxx = cap;
   if (gxx < 1) gxx = 1;
+  const long long nx = (long long)B * H * W * C, ng = (long long)B * npix * C;
   if (x_up2)
     bn_bwd_apply_kernel<1><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
-        (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg);
+        make_act(gy, ng), make_act(x, nx), mean_rstd, scale_ptr, row_stride, cls, M, make_act(residual, ng), make_act(gx, ng),
+        H, W, cg);
   else
     bn_bwd_apply_kernel<0><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
-        (const bf16*)gy, (const bf16*)x, mean_rstd, scale_ptr, row_stride, cls, M, (const bf16*)residual, (bf16*)gx, H, W, cg);
+        make_act(gy, ng), make_act(x, nx), mean_rstd, scale_ptr, row_stride, cls, M, make_act(residual, ng), make_act(gx, ng),
+        H, W, cg);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -691,7 +690,7 @@ extern "C" int spyr_up2_bwd(const void* g_hi, void* g_lo, int B, int H, int W, i
   SPYR_REQUIRE(H + W <= GATHER_MAX, "up2_bwd: H + W = %d exceeds the gather table (%d)", H + W, GATHER_MAX);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;  // the tables are built once per block: a few blocks per SM, grid-stride loop
-  up2_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)g_hi, (bf16*)g_lo, B, H, W, C / 8);
+  up2_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_act(g_hi, n * 32), make_act(g_lo, n * 8), B, H, W, C / 8);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

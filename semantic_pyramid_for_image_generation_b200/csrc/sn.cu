@@ -42,27 +42,27 @@ __device__ __forceinline__ int find_layer(const spyr_sn_layer* tab, int n, int t
   return *sh_idx;
 }
 
-constexpr int WTU_ROWS = 64, WTU_COLS = 256;
+constexpr int WTU_COLS = 64, WTU_GROUPS = 4;  // 256 threads: 64 columns x 4 interleaved row groups
 
-// t[j] += sum_{i in tile rows} W[i][j] u[i]
+// t[j] = sum_i W[i][j] u[i].  One CTA owns 64 columns and ALL rows of its layer: no sum crosses a CTA, so the result
+// does not depend on scheduling (the row groups of a CTA are combined in a fixed order).
 __global__ void sn_wtu_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch) {
   __shared__ int sh_idx;
-  __shared__ float su[WTU_ROWS];
+  __shared__ float part[WTU_GROUPS][WTU_COLS];
   const int l = find_layer(tab, n, blockIdx.x, 0, &sh_idx);
   const spyr_sn_layer L = tab[l];
-  const int tile = blockIdx.x - L.tile0_wtu;
-  const int ctiles = (L.cols + WTU_COLS - 1) / WTU_COLS;
-  const int r0 = (tile / ctiles) * WTU_ROWS, c0 = (tile % ctiles) * WTU_COLS;
-  const int nr = min(WTU_ROWS, L.rows - r0);
-  if (threadIdx.x < nr) su[threadIdx.x] = L.u[r0 + threadIdx.x];
-  __syncthreads();
-  const int j = c0 + threadIdx.x;
-  if (j >= L.cols) return;
-  const float* wp = L.w + (size_t)r0 * L.cols + j;
+  const int c0 = (blockIdx.x - L.tile0_wtu) * WTU_COLS;
+  const int cj = threadIdx.x % WTU_COLS, rg = threadIdx.x / WTU_COLS;
+  const int j = c0 + cj;
   float acc = 0.f;
+  if (j < L.cols) {
+    const float* wp = L.w + j;
 #pragma unroll 8
-  for (int i = 0; i < nr; ++i) acc += wp[(size_t)i * L.cols] * su[i];
-  atomicAdd(scratch + L.scratch_off + j, acc);
+    for (int i = rg; i < L.rows; i += WTU_GROUPS) acc += __ldg(wp + (size_t)i * L.cols) * __ldg(L.u + i);
+  }
+  part[rg][cj] = acc;
+  __syncthreads();
+  if (rg == 0 && j < L.cols) scratch[L.scratch_off + j] = (part[0][cj] + part[1][cj]) + (part[2][cj] + part[3][cj]);
 }
 
 constexpr int WV_ROWS = 8;  // one weight row per warp
@@ -120,7 +120,7 @@ __global__ void sn_wv_kernel(const spyr_sn_layer* __restrict__ tab, int n, float
 // sigma, u update, saved copies, BF16 pack.  One CTA per weight row (pack layers) or one CTA per layer.
 __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, const float* __restrict__ scratch,
                                int training, float eps, bf16* __restrict__ packed, float* __restrict__ stencil,
-                               float* __restrict__ saved) {
+                               float* __restrict__ saved, int split) {
   __shared__ int sh_idx;
   __shared__ float red[32];
   const int l = find_layer(tab, n, blockIdx.x, 2, &sh_idx);
@@ -154,6 +154,8 @@ __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, con
   const float inv = 1.f / sigma;
   bf16* dst = packed + L.pack_off;
   const int taps = L.taps, pc = L.pack_cin;
+  // split mode: the lo plane (bf16 of the rounding residual) follows the hi plane of the layer's pack
+  const size_t lo = split ? (size_t)L.rows * pc * (L.pack_mode == 1 ? 1 : taps) : 0;
   for (int co = tile * PACK_ROWS; co < min(L.rows, (tile + 1) * PACK_ROWS); ++co) {
     const float* wrow = L.w + (size_t)co * L.cols;
     if (L.pack_mode == 1) {
@@ -161,7 +163,9 @@ __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, con
       for (int k = threadIdx.x; k < pc; k += blockDim.x) {
         float v = 0.f;
         if (k < L.cols) v = wrow[(k % L.cin) * taps + k / L.cin] * inv;
-        dst[(size_t)co * pc + k] = __float2bfloat16(v);
+        const bf16 h = __float2bfloat16(v);
+        dst[(size_t)co * pc + k] = h;
+        if (lo) dst[lo + (size_t)co * pc + k] = __float2bfloat16(v - __bfloat162float(h));
       }
       continue;
     }
@@ -169,7 +173,10 @@ __global__ void sn_pack_kernel(const spyr_sn_layer* __restrict__ tab, int n, con
 #pragma unroll 4
     for (int i = threadIdx.x; i < taps * pc; i += blockDim.x) {
       const int t = i / pc, ci = i % pc;
-      dst[((size_t)t * L.rows + co) * pc + ci] = __float2bfloat16(__ldg(wrow + ci * taps + t) * inv);
+      const float v = __ldg(wrow + ci * taps + t) * inv;
+      const bf16 h = __float2bfloat16(v);
+      dst[((size_t)t * L.rows + co) * pc + ci] = h;
+      if (lo) dst[lo + ((size_t)t * L.rows + co) * pc + ci] = __float2bfloat16(v - __bfloat162float(h));
     }
     if (L.stencil_off >= 0 && threadIdx.x < 32) {
       // extra (mask) input channel pack_cin: FP32 taps + their sum
@@ -189,7 +196,8 @@ constexpr int BT = 32;  // backward tile: 32 rows (cout) x BTC input channels x 
 // single-tap layers (linear, 1x1, embedding) take 9x wider tiles so that every CTA moves the same ~9K elements
 __host__ __device__ inline int sn_btc(int taps) { return taps == 1 ? 9 * BT : BT; }
 
-// pass 1: dots[l] += sum G * W      pass 2: out = (G - dots/sigma * u v^T) / sigma
+// pass 1: dots[tile] = sum over the tile of G * W (one slot per CTA)
+// pass 2: out = (G - <G, W>/sigma * u v^T) / sigma, <G, W> = the layer's tile slots summed in a fixed order
 // TAPS is a compile-time copy of L.taps for the two shapes that carry all the bytes (1 and 9): the index split
 // e -> (ci, t) is then a multiply-shift instead of an integer division per element.
 template <int PASS, int TAPS>
@@ -246,10 +254,13 @@ __device__ __forceinline__ void sn_bwd_tile(const spyr_sn_layer& L, int tile, co
       }
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(dots + L.index, acc);
+    if (threadIdx.x == 0) dots[L.tile0_bwd + tile] = acc;
   } else {
     const float inv = 1.f / sigma;
-    const float coef = dots[L.index] * inv;  // <G, W/sigma>
+    const int ltiles = ((L.rows + BT - 1) / BT) * ctiles;
+    float dsum = 0.f;
+    for (int i = threadIdx.x; i < ltiles; i += blockDim.x) dsum += dots[L.tile0_bwd + i];
+    const float coef = block_sum(dsum, red) * inv;  // <G, W/sigma>
     float* out = grad_arena + L.grad_off;
     const float* vv = sv + 1 + L.rows + (size_t)ci0 * taps;
     for (int r = wid; r < nco; r += nw) {
@@ -294,7 +305,7 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     SPYR_REQUIRE(L.taps <= 9, "sn_plan: layer %d has %d taps", i, L.taps);
     L.index = i;
     L.tile0_wtu = t_wtu;
-    t_wtu += ceil_div(L.rows, WTU_ROWS) * ceil_div(L.cols, WTU_COLS);
+    t_wtu += ceil_div(L.cols, WTU_COLS);
     L.tile0_wv = t_wv;
     t_wv += ceil_div(L.rows, WV_ROWS);
     L.tile0_pack = t_pack;
@@ -306,6 +317,7 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     L.saved_off = saved;
     saved += 1 + L.rows + L.cols;
   }
+  SPYR_REQUIRE(WTU_COLS * WTU_GROUPS == 256, "sn_plan: power-iteration tile shape");
   out->tiles_wtu = t_wtu;
   out->tiles_wv = t_wv;
   out->tiles_pack = t_pack;
@@ -320,15 +332,15 @@ extern "C" int spyr_sn_forward(const spyr_sn_layer* dev_tab, int n, const spyr_s
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(dev_tab && plan && scratch && saved && n > 0, "sn_forward: bad arguments");
   if (training) {
-    SPYR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * plan->scratch_floats, stream));
-    sn_wtu_kernel<<<plan->tiles_wtu, WTU_COLS, 0, stream>>>(dev_tab, n, scratch);
+    sn_wtu_kernel<<<plan->tiles_wtu, WTU_COLS * WTU_GROUPS, 0, stream>>>(dev_tab, n, scratch);
     spyr_count_launch();
     SPYR_LAUNCH_CHECK();
   }
   sn_wv_kernel<<<plan->tiles_wv, 256, 0, stream>>>(dev_tab, n, scratch, training, eps);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
-  sn_pack_kernel<<<plan->tiles_pack, 128, 0, stream>>>(dev_tab, n, scratch, training, eps, (bf16*)packed, stencil, saved);
+  sn_pack_kernel<<<plan->tiles_pack, 128, 0, stream>>>(dev_tab, n, scratch, training, eps, (bf16*)packed, stencil, saved,
+                                                       spyr_split() ? 1 : 0);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -338,7 +350,6 @@ extern "C" int spyr_sn_backward(const spyr_sn_layer* dev_tab, int n, const spyr_
                                 const float* saved, float* dots, float* grad_arena, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(dev_tab && plan && gw_arena && saved && dots && grad_arena, "sn_backward: bad arguments");
-  SPYR_CHECK_CUDA(cudaMemsetAsync(dots, 0, sizeof(float) * n, stream));
   const size_t smem = (size_t)9 * (BT * (BT + 1) + 4) * sizeof(float);
   sn_bwd_kernel<1><<<plan->tiles_bwd, 256, smem, stream>>>(dev_tab, n, gw_arena, saved, dots, grad_arena);
   spyr_count_launch();

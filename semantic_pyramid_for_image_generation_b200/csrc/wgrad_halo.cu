@@ -11,8 +11,10 @@
 // (stride-byte-offset), and the two 64-row halves of the M=128 accumulator are
 //   * the two 64-channel chunks of a 128-channel block (leading-byte-offset = halo buffer size), or
 //   * for 64-channel inputs, two different taps (leading-byte-offset = distance of their windows).
-// Each (half, tap) accumulator lives in TMEM for the whole pixel loop; the epilogue adds it to the FP32 gradient with
-// red.global.add (the pixel range is split over CTAs so that the grid fills the 148 SMs).
+// Each (half, tap) accumulator lives in TMEM for the whole pixel loop.  The pixel range is split over CTAs so that the
+// grid fills the 148 SMs: split z stores its partial sum to slice z of a scratch buffer and a second kernel
+// (wgrad_reduce_kernel, conv_tc.cu) adds the slices in order; a single split adds to the gradient directly.  No
+// floating-point atomics: the result is bit-reproducible.
 #include "common.cuh"
 #include "../../include/spyramid_b200.h"
 
@@ -46,6 +48,8 @@ struct WHParams {
   int stage_bytes, stages, splits;
   uint32_t tmem_cols;
   float* dw;
+  float* partial;        // scratch [slices][taps*cin_stride*Cout] or nullptr (direct accumulation into dw)
+  int slice0;
 };
 
 struct WHMaps {
@@ -200,7 +204,8 @@ wgrad_halo_kernel(const __grid_constant__ WHMaps maps, const WHParams p) {
         __syncwarp();
       }
     } else if (warp >= 4) {
-      // ===== epilogue: TMEM -> red.global.add.f32 =====
+      // ===== epilogue: TMEM -> partial-sum slice (plain stores) or dw (single split: owner read-modify-write) =====
+      float* out = p.partial != nullptr ? p.partial + (size_t)(p.slice0 + (int)blockIdx.y) * 9 * p.cin_stride * p.Cout : p.dw;
       const int q = warp & 3;
       const int m = q * 32 + lane;
       mbar_wait(done_bar, 0);
@@ -208,26 +213,15 @@ wgrad_halo_kernel(const __grid_constant__ WHMaps maps, const WHParams p) {
       for (int g = 0; g < ngroups; ++g) {
         const int tap = (m < 64) ? groups[g].tap_lo : groups[g].tap_hi;
         const int ci = ci_base + ((m < 64) ? groups[g].ci_lo : groups[g].ci_hi) + (m & 63);
-        const bool valid = tap >= 0 && ci < p.Cin;
+        const bool valid = tap >= 0 && ci < p.Cin && ci < p.cin_stride;
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + (uint32_t)(g * p.bn_cols) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
           tmem_ld_wait();
           if (!valid) continue;
           const int col0 = n_off + c0;
-          float* dst = p.dw + ((size_t)tap * p.cin_stride + ci) * p.Cout + col0;
-          if (col0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            // 16-byte vector reductions (sm_90+): a quarter of the L2 atomic transactions
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              atomicAdd(reinterpret_cast<float4*>(dst + j),
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                    __uint_as_float(r[j + 3])));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Cout) atomicAdd(dst + j, __uint_as_float(r[j]));
-          }
+          float* dst = out + ((size_t)tap * p.cin_stride + ci) * p.Cout + col0;
+          wgrad_store32(dst, r, p.Cout - col0, p.partial == nullptr);
         }
       }
     }
@@ -248,12 +242,13 @@ uint32_t pow2_at_least(int n, uint32_t lo) {
 
 }  // namespace
 
-// Returns 0 on launch, -1 if the problem is not eligible (caller uses the per-tap kernel), >0 on error.
-int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream) {
+// Fills the launch plan; returns 0 when the halo-tiled kernel takes the problem, -1 if it is not eligible (the caller uses
+// the per-tap kernel), >0 on error.
+static int halo_plan(const spyr_wgrad_desc* d, WHParams* pp) {
+  WHParams& p = *pp;
   if (d->ksize != 3 || d->per_image) return -1;
   if (d->H < 16 || d->W < 8 || (d->H % 16) != 0 || (d->W % 8) != 0) return -1;
   if ((d->Cin % 64) != 0 || (d->Cout % 8) != 0) return -1;
-  WHParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.cin_stride = d->cin_stride > 0 ? d->cin_stride : d->Cin;
@@ -290,20 +285,43 @@ int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream) {
   if (splits > p.ptiles) splits = p.ptiles;
   // short pixel loops cannot fill the 2..5-stage pipeline: small maps stay on the per-tap kernel (64-pixel steps)
   if (d->splits <= 0 && p.ptiles / splits < 6) return -1;
+  {
+    // every split owns at least one pixel tile (its slice of the partial sums is read unconditionally)
+    const int per = ceil_div(p.ptiles, splits);
+    splits = ceil_div(p.ptiles, per);
+  }
   p.splits = splits;
   p.dw = d->dw;
+  return 0;
+}
+
+int spyr_wgrad_halo_plan(const spyr_wgrad_desc* d, int* splits) {
+  WHParams p;
+  const int rc = halo_plan(d, &p);
+  if (rc == 0) *splits = p.splits;
+  return rc;
+}
+
+int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, const void* x, const void* dy, float* partial, int slice0,
+                           cudaStream_t stream) {
+  WHParams p;
+  const int rc = halo_plan(d, &p);
+  if (rc) return rc > 0 ? rc : 2;
+  p.partial = partial;
+  p.slice0 = slice0;
+  const int stages = p.stages, splits = p.splits;
   WHMaps maps;
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
     uint32_t box[4] = {64, 10, 18, 1};
-    if (spyr_tmap_encode(&maps.x, d->x, 4, dims, strides, box, 1)) return 3;
+    if (spyr_tmap_encode(&maps.x, x, 4, dims, strides, box, 1)) return 3;
   }
   {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t strides[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->W * d->Cout * 2, (uint64_t)d->H * d->W * d->Cout * 2};
     uint32_t box[4] = {64, 8, 16, 1};
-    if (spyr_tmap_encode(&maps.dy, d->dy, 4, dims, strides, box, 1)) return 3;
+    if (spyr_tmap_encode(&maps.dy, dy, 4, dims, strides, box, 1)) return 3;
   }
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   static bool configured = false;

@@ -70,17 +70,45 @@ class GradientReducer(object):
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
 
+    @staticmethod
+    def grads_alias_arena(module, arena) -> bool:
+        """True when every existing `.grad` of `module` is a view into `arena` at its GradArena offset.  That is what
+        autograd leaves behind after a backward from zeroed (set_to_none) gradients; it does NOT hold after
+        `zero_grad(set_to_none=False)`, gradient accumulation over several backwards, or a gradient hook that replaces
+        the tensor -- then the arena is a dead buffer and must not be what gets averaged."""
+        ga = getattr(module, "_ga", None)
+        if ga is None or arena is None:
+            return False
+        base = arena.data_ptr()
+        seen = False
+        for p, off in zip(ga.params, ga.offset_list):
+            if p.grad is None:
+                continue
+            seen = True
+            if p.grad.data_ptr() != base + 4 * off or p.grad.dtype != arena.dtype:
+                return False
+        return seen
+
     def average(self, module, wait: bool = True) -> None:
-        """Averages the gradients of `module`: the flat arena of the last backward when there is one, else per tensor."""
+        """Averages the gradients of `module` over the ranks: ONE collective sequence over the flat arena of the last
+        backward when the `.grad` tensors are views of it (checked), else one all-reduce per gradient tensor."""
         if not self.active:
             return
         arena = getattr(module, "_last_grad_arena", None)
-        if arena is not None:
+        if arena is not None and self.grads_alias_arena(module, arena):
             self.average_flat(arena, wait=wait)
             return
         for p in module.parameters():
             if p.grad is not None:
                 self.average_flat(p.grad.view(-1), wait=wait)
+
+    def broadcast_module(self, module, src: int = 0) -> None:
+        """Parameters and buffers of rank `src` to every rank (what nn.DataParallel's per-forward `replicate` guaranteed,
+        main.py:91-94): replicas then start identical whatever seed each process used."""
+        if not self.active:
+            return
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=self.group)
 
     def max_over_ranks(self, value: float, device=None) -> float:
         if not self.active:

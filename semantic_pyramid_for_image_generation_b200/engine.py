@@ -17,31 +17,56 @@ BF16 = torch.bfloat16
 
 
 class GradArena(object):
-    """Flat FP32 gradient storage for all parameters of a module (offsets in floats, 64-float aligned)."""
+    """Flat FP32 gradient storage for all parameters of a module (offsets in floats, 64-float aligned).
+
+    Offsets are kept per position in `module.parameters()` and resolved through the module's CURRENT parameter objects,
+    so a `copy.deepcopy` of the module (an EMA copy, say) or a `module.to(...)` that re-creates parameters keeps working:
+    the id -> position map is rebuilt whenever the parameter objects are not the ones it was built from."""
 
     def __init__(self, module):
-        self.params = list(module.parameters())
-        self.offsets = {}
+        self.module = module
+        self.sizes = [p.numel() for p in module.parameters()]
+        self.offset_list = []
         off = 0
-        for p in self.params:
-            self.offsets[id(p)] = off
-            off += (p.numel() + 63) // 64 * 64
+        for n in self.sizes:
+            self.offset_list.append(off)
+            off += (n + 63) // 64 * 64
         self.total = max(off, 64)
+        self._index = None
+        self._params = None
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = GradArena.__new__(GradArena)
+        new.module = copy.deepcopy(self.module, memo)  # memo holds the copy being built: no second copy is made
+        new.sizes, new.offset_list, new.total = list(self.sizes), list(self.offset_list), self.total
+        new._index = new._params = None
+        return new
+
+    @property
+    def params(self):
+        cur = list(self.module.parameters())
+        if self._params is None or len(cur) != len(self._params) or any(a is not b for a, b in zip(cur, self._params)):
+            if [p.numel() for p in cur] != self.sizes:
+                raise RuntimeError("the parameter list of the module changed shape since construction")
+            self._params = cur
+            self._index = {id(p): i for i, p in enumerate(cur)}
+        return self._params
+
+    def offset(self, param):
+        self.params  # refresh the id map if the parameter objects changed
+        return self.offset_list[self._index[id(param)]]
 
     def new(self, device):
         return torch.zeros(self.total, dtype=F32, device=device)
 
     def ptr(self, arena, param):
-        return arena.data_ptr() + 4 * self.offsets[id(param)]
+        return arena.data_ptr() + 4 * self.offset(param)
 
     def views(self, arena, needs):
         out = []
-        for p, need in zip(self.params, needs):
-            if need:
-                o = self.offsets[id(p)]
-                out.append(arena[o:o + p.numel()].view(p.shape))
-            else:
-                out.append(None)
+        for p, o, need in zip(self.params, self.offset_list, needs):
+            out.append(arena[o:o + p.numel()].view(p.shape) if need else None)
         return out
 
 
@@ -58,7 +83,8 @@ FUSED_ATTENTION = True  # tests flip this to compare the fused kernel with the p
 
 
 def fused_attention_ok(hw, d, nk, dv):
-    return FUSED_ATTENTION and hw % 128 == 0 and 8 <= d <= 64 and d % 8 == 0 and nk % 64 == 0 and 64 <= nk <= 256 \
+    # split-BF16 mode: the fused kernel keeps P in single-plane BF16 -> per-image GEMMs on (hi, lo) operands instead
+    return FUSED_ATTENTION and not ops.SPLIT and hw % 128 == 0 and 8 <= d <= 64 and d % 8 == 0 and nk % 64 == 0 and 64 <= nk <= 256 \
         and dv in (64, 128)
 
 
@@ -72,19 +98,19 @@ def attention_forward(att, key, st, x, want_act, save):
                     bias=att.value_convolution.bias)
     if fused_attention_ok(H * W, d, nk, dv):
         # one kernel: S = Q K^T, softmax over keys, O = P V; the attention map is written once (BF16) only for backward
-        Pm = torch.empty((B, H, W, nk), dtype=BF16, device=x.device) if save else None
-        O = torch.empty((B, H, W, dv), dtype=BF16, device=x.device)
+        Pm = ops.act_empty((B, H, W, nk), x.device) if save else None
+        O = ops.act_empty((B, H, W, dv), x.device)
         call("spyr_sagan_attention_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), O.data_ptr(), ptr(Pm), B, H * W, d, nk, dv)
     else:
         S = torch.empty((B, H * W, nk), dtype=F32, device=x.device)
         ops.conv(B, H, W, nk, [Src(q, k, d, 1, per_image=True)], f32_out=S, f32_store=True)
-        Pm = torch.empty((B, H, W, nk), dtype=BF16, device=x.device)
+        Pm = ops.act_empty((B, H, W, nk), x.device)
         call("spyr_softmax_rows_fwd", S.data_ptr(), Pm.data_ptr(), B * H * W, nk)
         O, _ = ops.conv(B, H, W, dv, [Src(Pm, v, nk, 1, mn=True, per_image=True)])
     t, _ = ops.conv(B, H, W, Cc, [Src(O, st.w(key + ".attention_convolution"), dv, 1)],
                     bias=att.attention_convolution.bias)
-    out = torch.empty_like(x)
-    out_act = torch.empty_like(x) if want_act else None
+    out = ops.act_like(x)
+    out_act = ops.act_like(x) if want_act else None
     call("spyr_gamma_residual_fwd", t.data_ptr(), x.data_ptr(), att.gamma.data_ptr(), out.data_ptr(), ptr(out_act), LRELU,
          x.numel())
     ctx = (x, xp, q, k, v, Pm, O, t) if save else None
@@ -97,9 +123,10 @@ def attention_backward(att, key, st, sn, ga, gw, grad, ctx, g_out, want_wgrad=Tr
     B, H, W, Cc = x.shape
     d, dv, nk = Cc // 8, Cc // 2, (H * W) // 4
     dev = x.device
-    gt = torch.empty_like(g_out)
+    gt = ops.act_like(g_out)
+    sc = ops.scratch(1, dev)
     call("spyr_gamma_residual_bwd", g_out.data_ptr(), t.data_ptr(), att.gamma.data_ptr(), gt.data_ptr(),
-         ga.ptr(grad, att.gamma), g_out.numel())
+         ga.ptr(grad, att.gamma), g_out.numel(), sc.data_ptr())
     ko = key + ".attention_convolution"
     if want_wgrad:
         ops.wgrad(O, gt, sn.gw_ptr(gw, ko), B, H, W, dv, Cc, 1)
@@ -110,7 +137,7 @@ def attention_backward(att, key, st, sn, ga, gw, grad, ctx, g_out, want_wgrad=Tr
     ops.wgrad(Pm, gO, dV.data_ptr(), B, H, W, nk, dv, 1, per_image=True)
     dP = torch.empty((B, H * W, nk), dtype=F32, device=dev)
     ops.conv(B, H, W, nk, [Src(gO, v, dv, 1, per_image=True)], f32_out=dP, f32_store=True)
-    dS = torch.empty((B, H, W, nk), dtype=BF16, device=dev)
+    dS = ops.act_empty((B, H, W, nk), dev)
     call("spyr_softmax_rows_bwd", Pm.data_ptr(), dP.data_ptr(), dS.data_ptr(), B * H * W, nk)
     gq, _ = ops.conv(B, H, W, d, [Src(dS, k, nk, 1, mn=True, per_image=True)])
     dK = torch.zeros((B, nk, d), dtype=F32, device=dev)
@@ -151,14 +178,15 @@ def _cbn_backward(cbn, ga, grad, x, mr, cls, g, mode, residual=None):
     emb = cbn.embedding.weight
     sp, hp = emb.data_ptr(), emb.data_ptr() + 4 * Cc
     S = torch.empty((B, 2, Cc), dtype=F32, device=x.device)
-    gy = torch.empty_like(x) if mode else g
+    gy = ops.act_like(x) if mode else g
+    sc = ops.scratch(2 * Cc, x.device)
     call("spyr_bn_bwd_reduce", g.data_ptr(), x.data_ptr(), mr.data_ptr(), sp, hp, 2 * Cc, cls.data_ptr(), LRELU, mode,
-         gy.data_ptr() if mode else None, S.data_ptr(), B, H, W, Cc)
+         gy.data_ptr() if mode else None, S.data_ptr(), B, H, W, Cc, sc.data_ptr())
     M = torch.empty(2 * Cc, dtype=F32, device=x.device)
     ge = ga.ptr(grad, emb)
     call("spyr_bn_bwd_finalize", S.data_ptr(), B, Cc, float(B * H * W), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(), ge,
          ge + 4 * Cc)
-    gx = torch.empty_like(x)
+    gx = ops.act_like(x)
     call("spyr_bn_bwd_apply", gy.data_ptr(), x.data_ptr(), mr.data_ptr(), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(),
          ptr(residual), gx.data_ptr(), B, H, W, Cc, 0)
     return gx
@@ -203,21 +231,42 @@ def _gblock_backward(blk, key, st, sn, ga, gw, grad, ctx, cls, g_out):
     ops.colsum(g_h1, Cout, ga.ptr(grad, c3.bias))
     g_a, _ = ops.conv(B, H2, W2, Cin, [Src(g_h1, st.w(k3), Cout, 3, mn=True)])
     # skip path: up2^T commutes with the 1x1 conv, so transpose-upsample the Cout-channel gradient first
-    g_lo = torch.empty((B, H, W, Cout), dtype=BF16, device=x.device)
+    g_lo = ops.act_empty((B, H, W, Cout), x.device)
     call("spyr_up2_bwd", g_out.data_ptr(), g_lo.data_ptr(), B, H, W, Cout)
     g_skip, _ = ops.conv(B, H, W, Cin, [Src(g_lo, st.w(kr), Cout, 1, mn=True)])
     return _cbn_backward(blk.main_block[0], ga, grad, x, mr1, cls, g_a, 1, residual=g_skip)
 
 
+def _mask_for(mask, batch, shape_tail, what):
+    """FP32 contiguous mask of `batch` rows; batch-1 masks (get_masks_for_inference(add_batch_size=True), misc.py:86-96)
+    broadcast like the reference's `features * masks`; anything else that does not match raises instead of letting a
+    kernel read out of bounds."""
+    m = mask if mask.dtype == F32 else mask.float()
+    if m.shape[0] == 1 and batch > 1:
+        m = m.expand(batch, *m.shape[1:])
+    if m.shape[0] != batch or m.numel() != batch * shape_tail:
+        raise RuntimeError("%s: mask of shape %s does not match batch %d x %d elements" %
+                           (what, tuple(mask.shape), batch, shape_tail))
+    return m.contiguous()
+
+
 def generator_forward(G, z, features, masks, class_id, save):
     training = G.training
+    if save and not training:
+        raise RuntimeError("Generator: backward through an eval()-mode forward is not implemented (the batch-norm backward "
+                           "kernels assume batch statistics); call .train() or wrap the call in torch.no_grad()")
     sn = G._sn
     st = sn.forward(training)
     B = z.shape[0]
+    if class_id.shape[0] != B:
+        raise RuntimeError("Generator: class_id batch %d does not match the latent batch %d" % (class_id.shape[0], B))
     cls = ops.argmax_rows(class_id)
     z = _f32c(z)
     f6, f5 = _f32c(features[6]), _f32c(features[5])
-    m6, m5 = _f32c(masks[6]), _f32c(masks[5])
+    if f6.shape[0] != B or f5.shape[0] != B:
+        raise RuntimeError("Generator: feature batch does not match the latent batch %d" % B)
+    m6 = _mask_for(masks[6], B, f6.shape[1], "Generator (logits level)")
+    m5 = _mask_for(masks[5], B, f5.shape[1], "Generator (fc7 level)")
     lb1, lb2 = G.linear_block_1, G.linear_block_2
     h0 = ops.linear_fwd(z, G.linear_layer.weight_orig, st.sigma("linear_layer"), G.linear_layer.bias)
     t1 = ops.linear_fwd(f6, lb1.masked_feature_mapping.weight_orig, st.sigma("linear_block_1.masked_feature_mapping"),
@@ -240,7 +289,8 @@ def generator_forward(G, z, features, masks, class_id, save):
         if idx == 3:
             x, _, c = attention_forward(layer, key, st, x, False, save)
         else:
-            mask = _f32c(masks[level])
+            hw = 4 * x.shape[1] * x.shape[2]  # the block's output resolution = the feature level's
+            mask = _mask_for(masks[level], B, hw, "Generator (pyramid level %d)" % level)
             x, c = _gblock_forward(layer, key, st, x, features[level], mask, cls, training, save)
             level -= 1
         block_ctx.append(c)
@@ -287,10 +337,11 @@ def generator_backward(G, ctx, g_img):
     f3, f5_ = G.final_block[3], G.final_block[5]
     bn = G.final_block[1]
     oc = f5_.shape[0]
-    g_h3 = torch.empty_like(a3)
+    g_h3 = ops.act_like(a3)
+    sc = ops.scratch(oc * c5 + oc, dev)
     call("spyr_conv1x1_tanh_bwd", g_img.data_ptr(), img.data_ptr(), a3.data_ptr(), f5_.weight_orig.data_ptr(),
          st.sigma("final_block.5"), LRELU, g_h3.data_ptr(), sn.gw_ptr(gw, "final_block.5"), ga.ptr(grad, f5_.bias), B,
-         4 * H * W, c5, oc)
+         4 * H * W, c5, oc, sc.data_ptr())
     ops.wgrad(a, g_h3, sn.gw_ptr(gw, "final_block.3"), B, 2 * H, 2 * W, c5, c5, 3)
     ops.colsum(g_h3, c5, ga.ptr(grad, f3.bias))
     g_pre, _ = ops.conv(B, 2 * H, 2 * W, c5, [Src(g_h3, st.w("final_block.3"), c5, 3, mn=True)], dmask=a,
@@ -300,15 +351,16 @@ def generator_backward(G, ctx, g_img):
     xu = ctx.get("xu")
     # training forward: BN ran on the materialised up2(x) -> plain reductions at 2H x 2W; eval forward: x interpolated
     xs, hs, ws, mode = (xu, 2 * H, 2 * W, 0) if xu is not None else (x, H, W, 3)
+    sc2 = ops.scratch(2 * c5, dev)
     call("spyr_bn_bwd_reduce", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, bp, 0, None, LRELU, mode, None,
-         S.data_ptr(), B, hs, ws, c5)
+         S.data_ptr(), B, hs, ws, c5, sc2.data_ptr())
     M = torch.empty(2 * c5, dtype=F32, device=dev)
     call("spyr_bn_bwd_finalize", S.data_ptr(), B, c5, float(B * 4 * H * W), wp, 0, None, M.data_ptr(),
          ga.ptr(grad, bn.weight), ga.ptr(grad, bn.bias))
-    g_hi = torch.empty_like(g_pre)
+    g_hi = ops.act_like(g_pre)
     call("spyr_bn_bwd_apply", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, 0, None, M.data_ptr(), None,
          g_hi.data_ptr(), B, hs, ws, c5, 0 if xu is not None else 1)
-    g = torch.empty_like(x)
+    g = ops.act_like(x)
     call("spyr_up2_bwd", g_hi.data_ptr(), g.data_ptr(), B, H, W, c5)
     del g_hi, g_pre, g_h3
     for idx in range(len(G.main_path) - 1, -1, -1):
@@ -405,11 +457,11 @@ def discriminator_forward(D, img, class_id, save):
     blk0 = D.layers[0]
     c0, c2, cr = blk0.main_block[0], blk0.main_block[2], blk0.residual_mapping
     C0 = c0.shape[0]
-    col = torch.empty((B, H, W, 32), dtype=BF16, device=dev)
+    col = ops.act_empty((B, H, W, 32), dev)
     call("spyr_im2col3x3", img.data_ptr(), B, H, W, None, None, col.data_ptr())
     _, h0 = ops.conv(B, H, W, C0, [Src(col, st.w("layers.0.main_block.0"), 32, 1)], bias=c0.bias, want_raw=False,
                      want_act=True)
-    xp8 = torch.empty((B, H // 2, W // 2, 8), dtype=BF16, device=dev)
+    xp8 = ops.act_empty((B, H // 2, W // 2, 8), dev)
     call("spyr_img_avgpool_pad8", img.data_ptr(), B, H, W, xp8.data_ptr())
     r, _ = ops.conv(B, H // 2, W // 2, C0, [Src(xp8, st.w("layers.0.residual_mapping"), 8, 1)], bias=cr.bias)
     if ops.can_pool(H, W, C0):
@@ -471,7 +523,7 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
         ops.linear_bwd_w(g_feat, feat0, sn.gw_ptr(gw, "layers.11"), ga.ptr(grad, l11.bias), y=feat, out_slope=LRELU)
     g_feat0 = ops.linear_bwd_x(g_feat, l11.weight_orig, st.sigma("layers.11"), y=feat, out_slope=LRELU)
     Bx, h, w, C7 = x7.shape
-    g = torch.empty_like(x7)
+    g = ops.act_like(x7)
     call("spyr_global_avgpool_lrelu_bwd", x7.data_ptr(), g_feat0.data_ptr(), LRELU, g.data_ptr(), B, h * w, C7)
     for idx in range(7, 0, -1):
         key = "layers.%d" % idx

@@ -14,6 +14,15 @@ F32 = torch.float32
 BF16 = torch.bfloat16
 
 
+def _batch_mask(m, batch):
+    """Masks built by get_masks_for_inference(add_batch_size=True) have batch 1: broadcast like the reference's `*`."""
+    if m.shape[0] == batch:
+        return m
+    if m.shape[0] == 1:
+        return m.expand(batch, *m.shape[1:])
+    raise RuntimeError("mask batch %d does not match the feature batch %d" % (m.shape[0], batch))
+
+
 def _nhwc(t):
     """NCHW-shaped feature -> NHWC BF16 contiguous (zero-copy for the views VGG16 returns)."""
     from . import ops
@@ -25,18 +34,28 @@ class _RecLossFn(torch.autograd.Function):
     def forward(ctx, n, *tensors):
         reals, fakes, masks = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
         dev = fakes[0].device
+        from . import ops
         loss = torch.zeros(1, dtype=F32, device=dev)
+        sc = ops.scratch(1, dev)  # the level kernels run back to back on this stream: one scratch serves all of them
         saved = []
         for fr, ff, m in zip(reals, fakes, masks):
-            m = m.float().contiguous()
+            m = _batch_mask(m.float(), ff.shape[0]).contiguous()
             if ff.dim() == 4:
                 a, b = _nhwc(fr), _nhwc(ff)
                 B, H, W, C = b.shape
-                call("spyr_rec_level_fwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), B, H, W, C, loss.data_ptr())
+                if a.shape != b.shape or m.numel() != B * H * W:
+                    raise RuntimeError("SemanticReconstructionLoss: level shapes differ (real %s, fake %s, mask %s)" %
+                                       (tuple(a.shape), tuple(b.shape), tuple(m.shape)))
+                call("spyr_rec_level_fwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), B, H, W, C, loss.data_ptr(),
+                     sc.data_ptr())
                 saved.append((a, b, m))
             else:
                 a, b = fr.float().contiguous(), ff.float().contiguous()
-                call("spyr_rec_vec_fwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), a.shape[0], a.shape[1], loss.data_ptr())
+                if a.shape != b.shape or m.shape != b.shape:
+                    raise RuntimeError("SemanticReconstructionLoss: vector level shapes differ (real %s, fake %s, mask %s)" %
+                                       (tuple(a.shape), tuple(b.shape), tuple(m.shape)))
+                call("spyr_rec_vec_fwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), a.shape[0], a.shape[1], loss.data_ptr(),
+                     sc.data_ptr())
                 saved.append((a, b, m))
         ctx.saved, ctx.n = saved, n
         return loss
@@ -51,8 +70,9 @@ class _RecLossFn(torch.autograd.Function):
                 grads.append(None)
                 continue
             if b.dim() == 4:
+                from . import ops
                 B, H, W, C = b.shape
-                gff = torch.empty_like(b)
+                gff = ops.act_like(b)
                 call("spyr_rec_level_bwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), B, H, W, C, g.data_ptr(),
                      gff.data_ptr())
                 grads.append(gff.permute(0, 3, 1, 2))
@@ -96,7 +116,10 @@ class _DiversityFn(torch.autograd.Function):
         z_half = (z.shape[0] // 2) * (z.numel() // z.shape[0])
         work = torch.empty(2, dtype=F32, device=img.device)
         loss = torch.empty((), dtype=F32, device=img.device)
-        call("spyr_diversity_fwd", img.data_ptr(), img_half, z.data_ptr(), z_half, work.data_ptr(), loss.data_ptr())
+        from . import ops
+        sc = ops.scratch(2, img.device)
+        call("spyr_diversity_fwd", img.data_ptr(), img_half, z.data_ptr(), z_half, work.data_ptr(), loss.data_ptr(),
+             sc.data_ptr())
         ctx.img, ctx.work, ctx.img_half = img, work, img_half
         return loss
 

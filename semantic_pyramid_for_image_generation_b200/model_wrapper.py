@@ -108,7 +108,7 @@ class ModelWrapper(object):
             if z_d is None:
                 z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
             images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
-        if side is None or not isinstance(self.discriminator_loss, LSGANDiscriminatorLoss):
+        if side is None or type(self.discriminator_loss) is not LSGANDiscriminatorLoss:  # subclasses may override forward
             # a user-supplied loss couples the two predictions: D(real) still overlaps VGG -> G, one joint backward
             prediction_real = D(images_real, labels)
             if side is not None:
@@ -189,6 +189,12 @@ class ModelWrapper(object):
         """Runs the discriminator update then the generator update on one device-resident batch and returns the five
         loss scalars as device tensors (no host synchronisation).  `noise` optionally supplies the two latent batches."""
         z_d, z_g = noise if noise is not None else (None, None)
+        if self.reducer is not None and self.reducer.active and not self.__dict__.get("_replicas_synced", False):
+            # rank 0's weights and buffers to every rank once (nn.DataParallel re-broadcast them every forward,
+            # main.py:91-94): the replicas start identical even if the processes were seeded differently
+            for module in (self.generator, self.discriminator, self.vgg16):
+                self.reducer.broadcast_module(module)
+            self._replicas_synced = True
         features_real, loss_d_real, loss_d_fake = self._phase_discriminator(images_real, labels, masks, z_d)
         if self.reducer is not None and self.reducer.active:
             # D's gradient all-reduce runs on the collective stream while the generator forward (which does not use D)
@@ -331,6 +337,10 @@ class ModelWrapper(object):
         return fake_images
 
 
+def red_active(wrapper):
+    return wrapper.reducer is not None and wrapper.reducer.active
+
+
 class CapturedTrainingStep(object):
     """One training iteration as three CUDA graphs with the two gradient all-reduces between them:
 
@@ -361,6 +371,8 @@ class CapturedTrainingStep(object):
         with torch.cuda.graph(self.graph_a, pool=pool):
             self.features_real, l_real, l_fake = wrapper._phase_discriminator(self.images, self.labels, self.masks, None)
         self.d_arena = wrapper.discriminator._last_grad_arena
+        if red_active(wrapper) and not wrapper.reducer.grads_alias_arena(wrapper.discriminator, self.d_arena):
+            raise RuntimeError("captured step: the discriminator's .grad tensors are not views of its gradient arena")
         self.graph_b1 = None
         red = wrapper.reducer
         if red is not None and red.active:
@@ -376,6 +388,8 @@ class CapturedTrainingStep(object):
                 l_g, l_rec, l_div = wrapper._phase_generator(self.features_real, self.labels, self.masks, None, w_rec,
                                                              w_div)
         self.g_arena = wrapper.generator._last_grad_arena
+        if red_active(wrapper) and not wrapper.reducer.grads_alias_arena(wrapper.generator, self.g_arena):
+            raise RuntimeError("captured step: the generator's .grad tensors are not views of its gradient arena")
         with torch.cuda.graph(self.graph_c, pool=pool):
             wrapper.generator_optimizer.step()
         self.launches_per_step = _native.launch_count()

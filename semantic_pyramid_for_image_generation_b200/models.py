@@ -114,9 +114,18 @@ def _sn_holders(module):
 # ------------------------------------------------------------------------------------------------
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, z, class_id, nfeat, *rest):
+    def forward(ctx, module, grad_on, z, class_id, nfeat, *rest):
+        # grad_on: torch.is_grad_enabled() at the call site.  Inside Function.forward grad mode is always off and
+        # ctx.needs_input_grad only mirrors requires_grad, so without it a no_grad() forward would save (and, for the
+        # attention map, write) everything a backward needs.
         features, masks = rest[:nfeat], rest[nfeat:2 * nfeat]
-        save = any(ctx.needs_input_grad)
+        if grad_on and (ctx.needs_input_grad[2] or any(ctx.needs_input_grad[5:5 + nfeat])):
+            # the reference back-propagates into z and the features and discards the results (model_wrapper.py:168-190);
+            # this path does not compute them: refuse rather than hand back silently-zero gradients.  (Masks / class ids,
+            # which the reference's loader flags as requiring grad out of habit, data.py:80,87, are ignored.)
+            raise RuntimeError("Generator: gradients w.r.t. the latent input or the VGG features are not implemented "
+                               "(detach them; the reference never uses these gradients)")
+        save = grad_on and any(ctx.needs_input_grad)
         img, c = engine.generator_forward(module, z, features, masks, class_id, save)
         ctx.module, ctx.c = module, c
         return img
@@ -174,7 +183,7 @@ class Generator(nn.Module):
                 specs.append(LayerSpec(name, h, pack_cin=h.shape[1]))
             else:
                 specs.append(LayerSpec(name, h))  # FP32 consumers (linear layers, the C->3 tail): sigma only
-        self._sn = SNSet(specs, self._ga.offsets)
+        self._sn = SNSet(specs, self._ga.offset)
         self._last_grad_arena = None
 
     def forward(self, input: torch.Tensor, features: List[torch.Tensor],
@@ -193,7 +202,8 @@ class Generator(nn.Module):
                                "models.py:78,95)")
         if len(features) != 7 or len(masks) != 7:
             raise RuntimeError("Generator.forward expects 7 features and 7 masks")
-        return _GeneratorFn.apply(self, input, class_id, len(features), *features, *masks, *self._ga.params)
+        return _GeneratorFn.apply(self, torch.is_grad_enabled(), input, class_id, len(features), *features, *masks,
+                                  *self._ga.params)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,8 +211,8 @@ class Generator(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, img, class_id, *params):
-        save = any(ctx.needs_input_grad)
+    def forward(ctx, module, grad_on, img, class_id, *params):
+        save = grad_on and any(ctx.needs_input_grad)
         out, c = engine.discriminator_forward(module, img, class_id, save)
         ctx.module, ctx.c = module, c
         return out
@@ -210,8 +220,8 @@ class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         module = ctx.module
-        needs = ctx.needs_input_grad[3:]
-        grad, g_img = engine.discriminator_backward(module, ctx.c, g_out, any(needs), ctx.needs_input_grad[1])
+        needs = ctx.needs_input_grad[4:]
+        grad, g_img = engine.discriminator_backward(module, ctx.c, g_out, any(needs), ctx.needs_input_grad[2])
         ctx.c = None
         pg = [None] * len(needs)
         if grad is not None:
@@ -220,7 +230,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             task = getattr(torch._C, "_current_graph_task_id", lambda: -1)()
             same_pass = prev is not None and task >= 0 and getattr(module, "_grad_task", -1) == task
             earlier_pass = prev is not None and p0.grad is not None and \
-                p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offsets[id(p0)]
+                p0.grad.data_ptr() == prev.data_ptr() + 4 * ga.offset(p0)
             cur = torch.cuda.current_stream(grad.device)
             if all(needs) and prev is not None and prev.device == grad.device and (same_pass or earlier_pass):
                 # D(real) and D(fake) (model_wrapper.py:153-160) both feed every parameter.  The views of the first
@@ -239,7 +249,7 @@ class _DiscriminatorFn(torch.autograd.Function):
                 module._grad_task = task
                 module._grad_stream = cur
                 pg = module._ga.views(grad, needs)
-        return (None, g_img, None) + tuple(pg)
+        return (None, None, g_img, None) + tuple(pg)
 
 
 class Discriminator(nn.Module):
@@ -284,7 +294,7 @@ class Discriminator(nn.Module):
                 specs.append(LayerSpec(name, h, pack_cin=h.shape[1]))
             else:
                 specs.append(LayerSpec(name, h))
-        self._sn = SNSet(specs, self._ga.offsets)
+        self._sn = SNSet(specs, self._ga.offset)
         self._last_grad_arena = None
 
     def forward(self, input: torch.Tensor, class_id: torch.Tensor) -> torch.Tensor:
@@ -295,7 +305,7 @@ class Discriminator(nn.Module):
         :return: (torch.Tensor) Prediction of shape (B, B, 128)
         '''
         _require_cuda(input, "Discriminator.forward")
-        return _DiscriminatorFn.apply(self, input, class_id, *self._ga.params)
+        return _DiscriminatorFn.apply(self, torch.is_grad_enabled(), input, class_id, *self._ga.params)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -303,18 +313,21 @@ class Discriminator(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class _VGGFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, img):
+    def forward(ctx, module, grad_on, img):
         pk = module._pack()
-        pools, y7, y8, c = vgg_engine.vgg_forward(pk, img, ctx.needs_input_grad[1])
+        pools, y7, y8, c = vgg_engine.vgg_forward(pk, img, grad_on and ctx.needs_input_grad[2])
         ctx.pk, ctx.c = pk, c
         return tuple(pools) + (y7, y8)
 
     @staticmethod
     def backward(ctx, *grads):
+        from . import ops
         g_pools = [g.contiguous() if g is not None else None for g in grads[:5]]
+        # split-BF16 mode: a gradient that did not come from this package's kernels has no lo plane -> rebuild the pair
+        g_pools = [g if g is None or (g.dtype == BF16 and ops.has_planes(g)) else ops.to_act(g.float()) for g in g_pools]
         g_img = vgg_engine.vgg_backward(ctx.pk, ctx.c, g_pools, grads[5], grads[6])
         ctx.c = None
-        return None, g_img
+        return None, None, g_img
 
 
 class _VGGTrainFn(torch.autograd.Function):
@@ -367,7 +380,8 @@ class VGG16(nn.Module):
         self._dropout_calls = 0
 
     def _pack(self):
-        sig = tuple((p.data_ptr(), p._version) for p in self.vgg16.parameters())
+        from . import ops
+        sig = tuple((p.data_ptr(), p._version) for p in self.vgg16.parameters()) + (ops.SPLIT,)
         if self._pk is None or sig != self._pk_sig:
             self._pk = vgg_engine.VGGPack(self.vgg16)
             self._pk_sig = sig
@@ -398,7 +412,7 @@ class VGG16(nn.Module):
             raise RuntimeError("VGG16 in train() mode is the classifier fine-tuning path: construct it with "
                                "return_output=True and trainable parameters (vgg_16_train.py), or call .eval() as "
                                "model_wrapper.py:113 does for the frozen feature pyramid")
-        outs = _VGGFn.apply(self, input)
+        outs = _VGGFn.apply(self, torch.is_grad_enabled(), input)
         if self.return_output:
             return outs[6]
         return [t.permute(0, 3, 1, 2) for t in outs[:5]] + [outs[5], outs[6]]

@@ -15,6 +15,87 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 LRELU = 0.2
 
+# ------------------------------------------------------------------------------------------------
+# Precision mode (include/spyramid_b200.h, spyr_set_precision).  "bf16": BF16 operands / FP32 accumulate, one plane per
+# feature map (the throughput mode).  "split": every BF16 map is a (hi, lo) plane pair and the tensor cores compute
+# three products per convolution -- ~16 mantissa bits end to end, the mode in which network-level outputs meet the
+# reference's FP32 results within rel-L2 5e-3 (the "strict" mode of the parity tests).  Maps are torch tensors viewing
+# the hi plane; the lo plane follows it in the same allocation, which is why every map must come from `act_empty`.
+# ------------------------------------------------------------------------------------------------
+SPLIT = False
+
+
+def set_precision(mode):
+    """mode: "bf16" (default) or "split" / "strict".  Process-wide; switch only between forward/backward passes."""
+    global SPLIT
+    mode = {"fast": "bf16", "strict": "split"}.get(mode, mode)
+    if mode not in ("bf16", "split"):
+        raise ValueError("precision mode must be 'bf16' or 'split' (got %r)" % (mode,))
+    rc = N.lib().spyr_set_precision(1 if mode == "split" else 0)
+    if rc != 0:
+        raise RuntimeError("spyr_set_precision failed: %s" % N.lib().spyr_last_error().decode())
+    SPLIT = mode == "split"
+
+
+def precision():
+    return "split" if SPLIT else "bf16"
+
+
+if os.environ.get("SPYR_PRECISION"):
+    set_precision(os.environ["SPYR_PRECISION"])
+
+
+def act_empty(shape, device):
+    """Uninitialised BF16 feature map (or packed operand) of `shape`; in split mode the lo plane follows in the same storage."""
+    shape = tuple(int(v) for v in shape)
+    if SPLIT:
+        return torch.empty((2,) + shape, dtype=BF16, device=device)[0]
+    return torch.empty(shape, dtype=BF16, device=device)
+
+
+def act_zeros(shape, device):
+    shape = tuple(int(v) for v in shape)
+    if SPLIT:
+        return torch.zeros((2,) + shape, dtype=BF16, device=device)[0]
+    return torch.zeros(shape, dtype=BF16, device=device)
+
+
+def act_like(t):
+    return act_empty(t.shape, t.device)
+
+
+def has_planes(t):
+    """Whether the storage behind the contiguous BF16 map `t` holds what the current mode needs (split: a lo plane)."""
+    if not SPLIT:
+        return True
+    return t.untyped_storage().nbytes() >= 2 * (t.storage_offset() + 2 * t.numel())
+
+
+def to_act(values):
+    """FP32 tensor -> BF16 map in the current mode (split: hi = bf16(v), lo = bf16(v - hi)).  Host-side packing of frozen
+    operands (VGG weights); activations are converted by the kernels."""
+    values = values.float().contiguous()
+    out = act_empty(values.shape, values.device)
+    hi = values.to(BF16)
+    out.copy_(hi)
+    if SPLIT:
+        lo = torch.as_strided(out, out.shape, out.stride(), out.storage_offset() + out.numel())
+        lo.copy_((values - hi.float()).to(BF16))
+    return out
+
+
+def act_value(t):
+    """FP32 value of a map (hi + lo in split mode): for tests and debugging."""
+    v = t.float()
+    if SPLIT and has_planes(t):
+        v = v + torch.as_strided(t, t.shape, t.stride(), t.storage_offset() + t.numel()).float()
+    return v
+
+
+def scratch(n_outputs, device):
+    """Scratch of a deterministic grid reduction over `n_outputs` values (SPYR_REDUCE_SCRATCH_BYTES)."""
+    return torch.empty(N.REDUCE_BLOCKS * int(n_outputs) * 8, dtype=torch.uint8, device=device)
+
 # bench.py sets this to a list to time every tensor-core launch with CUDA events on the launching stream:
 # entries are (kernel, algorithmic_flops, algorithmic_bytes, start_event, end_event)
 PROFILE = None
@@ -62,6 +143,7 @@ class LeafStream(object):
         return True
 
     def run(self, tensors, name, *args):
+        """`tensors`: everything the call reads or writes that must outlive the enqueue (inputs, scratch)."""
         if self.active is None:
             call(name, *args)
             return
@@ -83,7 +165,7 @@ LEAF = LeafStream()
 
 
 def empty_bf16(*shape, device=None):
-    return torch.empty(shape, dtype=BF16, device=device or "cuda")
+    return act_empty(shape, device or "cuda")
 
 
 def empty_f32(*shape, device=None):
@@ -96,10 +178,11 @@ def zeros_f32(*shape, device=None):
 
 class Src(object):
     """One accumulation source of a tensor-core convolution (see spyr_conv_src)."""
-    __slots__ = ("x", "w", "cin", "ksize", "mn", "per_image")
+    __slots__ = ("x", "w", "cin", "ksize", "mn", "per_image", "w_lo_off")
 
-    def __init__(self, x, w, cin, ksize, mn=False, per_image=False):
+    def __init__(self, x, w, cin, ksize, mn=False, per_image=False, w_lo_off=0):
         self.x, self.w, self.cin, self.ksize, self.mn, self.per_image = x, w, cin, ksize, mn, per_image
+        self.w_lo_off = w_lo_off  # split mode: elements from w to its lo plane when not slices * Cout * cin
 
 
 def _run_fprop(d, srcs, B, H, W, Cout, out_bytes):
@@ -130,7 +213,7 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         # 64-wide input gradient: re-lay the (tiny) forward weights as a K-major operand with flipped taps so the layer
         # runs on the CTA-pair kernel (its MN-major form is limited to the single-CTA kernel)
         s0 = srcs[0]
-        wt = torch.empty((9, Cout, s0.cin), dtype=BF16, device=dev)
+        wt = act_empty((9, Cout, s0.cin), dev)
         call("spyr_weight_transpose_flip", s0.w if isinstance(s0.w, int) else s0.w.data_ptr(), wt.data_ptr(), 9, s0.cin, Cout)
         srcs = [Src(s0.x, wt, s0.cin, 3)]
     d = N.ConvDesc()
@@ -140,6 +223,7 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         d.src[i].w = s.w if isinstance(s.w, int) else s.w.data_ptr()
         d.src[i].cin, d.src[i].ksize = s.cin, s.ksize
         d.src[i].w_mn_major, d.src[i].w_per_image = int(s.mn), int(s.per_image)
+        d.src[i].w_lo_off = int(s.w_lo_off)
     d.bias = bias if isinstance(bias, int) else ptr(bias)
     d.bias2, d.bias3 = ptr(bias2), ptr(bias3)
     d.stencil_mask = ptr(stencil_mask)
@@ -154,17 +238,20 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         # accumulator and apply the fused epilogue in a second, tiny kernel
         ksteps = sum(((s.cin + 63) // 64) * s.ksize * s.ksize for s in srcs)
         tiles = ((npix + 127) // 128) * ((Cout + 255) // 256)
+        if SPLIT:
+            ksteps *= 3  # three operand products per source
         nsplit = max(1, min(ksteps // 4, 148 // tiles))
         if nsplit > 1:
-            acc = torch.zeros((npix, Cout), dtype=F32, device=dev)
+            # one FP32 slice per split, summed in split order by the epilogue kernel (no atomics: reproducible)
+            acc = torch.empty((nsplit, npix, Cout), dtype=F32, device=dev)
             d.y_f32, d.splits = acc.data_ptr(), nsplit
             _run_fprop(d, srcs, B, H, W, Cout, 4 * npix * Cout)
-            d.y_f32, d.splits = None, 0
+            d.y_f32 = None
             if want_raw:
-                y_raw = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+                y_raw = act_empty((B, H, W, Cout), dev)
                 d.y_raw = y_raw.data_ptr()
             if want_act:
-                y_act = torch.empty((B, H, W, Cout), dtype=BF16, device=dev)
+                y_act = act_empty((B, H, W, Cout), dev)
                 d.y_act = y_act.data_ptr()
             d.act, d.act_slope = act, act_slope
             call("spyr_conv2d_epilogue", C.byref(d), acc.data_ptr())
@@ -175,10 +262,10 @@ def conv(B, H, W, Cout, srcs, bias=None, bias2=None, bias3=None, stencil_mask=No
         oh, ow = (H // 2, W // 2) if pool else (H, W)
         d.pool = int(pool)
         if want_raw:
-            y_raw = torch.empty((B, oh, ow, Cout), dtype=BF16, device=dev)
+            y_raw = act_empty((B, oh, ow, Cout), dev)
             d.y_raw = y_raw.data_ptr()
         if want_act:
-            y_act = torch.empty((B, oh, ow, Cout), dtype=BF16, device=dev)
+            y_act = act_empty((B, oh, ow, Cout), dev)
             d.y_act = y_act.data_ptr()
         d.act, d.act_slope = act, act_slope
     out_bytes = (4 if f32_out is not None else 2) * npix * Cout * (int(want_raw) + int(want_act) if f32_out is None else 1)
@@ -190,7 +277,7 @@ def can_pool(H, W, Cout):
     """Whether conv(..., pool=True) applies: a halo-tiled map (>= 16x8, not the split-K small maps) and full 32-channel
     epilogue chunks."""
     return H >= 16 and W >= 8 and H % 16 == 0 and W % 8 == 0 and H * W >= 128 and Cout % 32 == 0 \
-        and os.environ.get("SPYR_POOL_FUSION", "1") != "0"
+        and os.environ.get("SPYR_POOL_FUSION", "1") != "0" and not SPLIT
 
 
 def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=False):
@@ -199,11 +286,17 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
     d.B, d.H, d.W, d.Cin, d.Cout, d.ksize = B, H, W, Cin, Cout, ksize
     d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw_ptr
     d.cin_stride, d.per_image = cin_stride, int(per_image)
+    # partial-sum slices of the pixel splits (summed in a fixed order by a second kernel: no atomics)
+    need = int(N.lib().spyr_conv2d_wgrad_scratch_floats(C.byref(d)))
+    if need < 0:
+        raise RuntimeError("spyr_conv2d_wgrad_scratch_floats: %s" % N.lib().spyr_last_error().decode())
+    sc = torch.empty(need, dtype=F32, device=x.device) if need > 0 else None
+    d.scratch, d.scratch_floats = ptr(sc), need
     if PROFILE is None:
         if per_image:
             call("spyr_conv2d_wgrad", C.byref(d))  # attention dK / dV feed the rest of the backward: not a leaf
         else:
-            LEAF.run((x, dy), "spyr_conv2d_wgrad", C.byref(d))
+            LEAF.run((x, dy, sc), "spyr_conv2d_wgrad", C.byref(d))
     else:
         npx = B * H * W
         _profiled("conv_wgrad_kernel", 2.0 * npx * Cin * Cout * ksize * ksize,
@@ -213,23 +306,26 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
 
 def colsum(g, C_, out0, out1=None, out2=None):
     rows = g.numel() // C_
-    LEAF.run((g,), "spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2)
+    sc = scratch(C_, g.device)
+    LEAF.run((g, sc), "spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2, sc.data_ptr())
 
 
 def stencil_wgrad(mask, dy, B, H, W, Cout, gw_ptr, cin_stride, cin_index):
     """Weight gradient of the mask channel of cat(feature*mask, mask) (models.py:94): nine masked sums of dy."""
-    LEAF.run((mask, dy), "spyr_stencil_wgrad", mask.data_ptr(), dy.data_ptr(), B, H, W, Cout, gw_ptr, cin_stride, cin_index)
+    sc = scratch(9 * Cout, dy.device)
+    LEAF.run((mask, dy, sc), "spyr_stencil_wgrad", mask.data_ptr(), dy.data_ptr(), B, H, W, Cout, gw_ptr, cin_stride,
+             cin_index, sc.data_ptr())
 
 
 def maskgate(f, mask):
-    out = torch.empty_like(f)
+    out = act_like(f)
     call("spyr_maskgate", f.data_ptr(), mask.data_ptr(), out.data_ptr(), f.numel() // f.shape[-1], f.shape[-1])
     return out
 
 
 def nchw_to_nhwc(src, mask=None, slope=1.0):
     B, Cc, H, W = src.shape
-    out = torch.empty((B, H, W, Cc), dtype=BF16, device=src.device)
+    out = act_empty((B, H, W, Cc), src.device)
     call("spyr_nchw_to_nhwc", src.data_ptr(), ptr(mask), slope, out.data_ptr(), B, Cc, H * W)
     return out
 
@@ -246,7 +342,7 @@ def as_nhwc_bf16(t, mask=None):
     converted (FP32 NCHW -> BF16 NHWC).  The optional (B,1,H,W) mask gates the feature (models.py:94)."""
     if t.dtype == BF16 and t.dim() == 4:
         v = t.permute(0, 2, 3, 1)
-        if v.is_contiguous():
+        if v.is_contiguous() and has_planes(v):  # split mode: only maps of this package carry their lo plane
             return maskgate(v, mask) if mask is not None else v
     if t.dtype != F32 or not t.is_contiguous():
         t = t.float().contiguous()
@@ -255,22 +351,22 @@ def as_nhwc_bf16(t, mask=None):
 
 def avgpool2(x, residual=None, want_raw=True, want_act=False, slope=LRELU):
     B, H, W, Cc = x.shape
-    y_raw = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device) if want_raw else None
-    y_act = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device) if want_act else None
+    y_raw = act_empty((B, H // 2, W // 2, Cc), x.device) if want_raw else None
+    y_act = act_empty((B, H // 2, W // 2, Cc), x.device) if want_act else None
     call("spyr_avgpool2_fwd", x.data_ptr(), ptr(residual), ptr(y_raw), ptr(y_act), slope, B, H, W, Cc)
     return y_raw, y_act
 
 
 def avgpool2_bwd(g_lo):
     B, h, w, Cc = g_lo.shape
-    g_hi = torch.empty((B, 2 * h, 2 * w, Cc), dtype=BF16, device=g_lo.device)
+    g_hi = act_empty((B, 2 * h, 2 * w, Cc), g_lo.device)
     call("spyr_avgpool2_bwd", g_lo.data_ptr(), g_hi.data_ptr(), B, 2 * h, 2 * w, Cc)
     return g_hi
 
 
 def maxpool2(x):
     B, H, W, Cc = x.shape
-    y = torch.empty((B, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    y = act_empty((B, H // 2, W // 2, Cc), x.device)
     call("spyr_maxpool2_fwd", x.data_ptr(), y.data_ptr(), B, H, W, Cc)
     return y
 
@@ -278,7 +374,7 @@ def maxpool2(x):
 def maxpool2_bwd(x, gy, relu_gate, out=None):
     B, H, W, Cc = x.shape
     acc = out is not None
-    gx = out if acc else torch.empty_like(x)
+    gx = out if acc else act_like(x)
     call("spyr_maxpool2_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), B, H, W, Cc, int(relu_gate), int(acc))
     return gx
 
@@ -286,16 +382,18 @@ def maxpool2_bwd(x, gy, relu_gate, out=None):
 def bn_stats(x, up2=False):
     B, H, W, Cc = x.shape
     sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
-    call("spyr_bn_stats", x.data_ptr(), B, H, W, Cc, int(up2), sums.data_ptr())
+    sc = scratch(2 * Cc, x.device)
+    call("spyr_bn_stats", x.data_ptr(), B, H, W, Cc, int(up2), sums.data_ptr(), sc.data_ptr())
     return sums
 
 
 def up2_stats(x):
     """xu = up2(x) (bilinear, align_corners=True) materialised in BF16 together with its per-channel sum / sum of squares."""
     B, H, W, Cc = x.shape
-    xu = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
+    xu = act_empty((B, 2 * H, 2 * W, Cc), x.device)
     sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
-    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), sums.data_ptr())
+    sc = scratch(2 * Cc, x.device)
+    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), sums.data_ptr(), sc.data_ptr())
     return xu, sums
 
 
@@ -309,8 +407,8 @@ def bn_finalize(sums, count, Cc, eps, momentum, running_mean, running_var, nbt, 
 def bn_act(x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, mode, want_xu=False, slope=LRELU):
     B, H, W, Cc = x.shape
     f = 2 if mode else 1
-    a = torch.empty((B, H * f, W * f, Cc), dtype=BF16, device=x.device)
-    xu = torch.empty((B, H * f, W * f, Cc), dtype=BF16, device=x.device) if want_xu else None
+    a = act_empty((B, H * f, W * f, Cc), x.device)
+    xu = act_empty((B, H * f, W * f, Cc), x.device) if want_xu else None
     call("spyr_bn_act", x.data_ptr(), mean_rstd.data_ptr(), scale_ptr, shift_ptr, row_stride, ptr(cls), slope, mode,
          a.data_ptr(), ptr(xu), B, H, W, Cc)
     return a, xu
@@ -353,6 +451,6 @@ def argmax_rows(onehot):
 
 
 def cast_bf16(src):
-    out = torch.empty(src.shape, dtype=BF16, device=src.device)
+    out = act_empty(src.shape, src.device)
     call("spyr_cast_f32_bf16", src.data_ptr(), out.data_ptr(), src.numel())
     return out

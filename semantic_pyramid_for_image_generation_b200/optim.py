@@ -37,6 +37,10 @@ class FusedAdam(torch.optim.Optimizer):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
+            # the kernel writes through raw pointers: tell autograd / version-keyed caches (VGG16._pack) that the
+            # parameters changed.  Under CUDA-graph replay this Python code does not run; consumers that cache derived
+            # operands across replays must not rely on versions (the GAN path re-reads weight_orig every forward).
+            torch._C._increment_version(params)
             dev = params[0].device
             counter = self._steps.get(gi)
             if counter is None or counter.device != dev:

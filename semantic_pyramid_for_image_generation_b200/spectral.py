@@ -83,41 +83,51 @@ class SNState(object):
 
 class SNSet(object):
     def __init__(self, specs, param_offsets):
-        """specs: list of LayerSpec in forward order; param_offsets: {id(param): float offset in the grad arena}."""
+        """specs: list of LayerSpec in forward order; param_offsets(param) -> float offset in the grad arena."""
         self.specs = specs
         self.by_key = {s.key: s for s in specs}
         self.param_offsets = param_offsets
         self.n = len(specs)
-        pack = sten = gw = 0
+        sten = gw = 0
         for s in specs:
-            if s.pack_cin > 0:
-                s.pack_off = pack
-                per = s.rows * s.pack_cin * (1 if s.pack_mode == 1 else s.taps)
-                pack += (per + 63) // 64 * 64
-            else:
-                s.pack_off = 0
+            s.pack_off = 0  # assigned per precision mode in _ensure_table
             if s.stencil:
                 s.stencil_off = sten
                 sten += 10 * s.rows
             else:
                 s.stencil_off = -1
-            s.gw_off = gw  # 16-byte aligned slices: the wgrad kernels reduce with float4 atomics
+            s.gw_off = gw  # 16-byte aligned slices: the wgrad kernels store float4 vectors
             gw += (s.rows * s.cols + 3) // 4 * 4
-        self.pack_elems, self.stencil_floats, self.gw_floats = pack, sten, gw
+        self.pack_elems, self.stencil_floats, self.gw_floats = 0, sten, gw
         self._ptr_sig = None
         self.host_tab = None
         self.dev_tab = None
         self.plan = N.SnPlan()
         self.scratch = None
 
+    def __deepcopy__(self, memo):
+        # the device/host tables hold raw pointers of the original module: a copy plans its own
+        import copy
+        return SNSet(copy.deepcopy(self.specs, memo), copy.deepcopy(self.param_offsets, memo))
+
     def _signature(self):
+        from . import ops
         return tuple(s.holder.weight_orig.data_ptr() for s in self.specs) + tuple(
-            s.holder.weight_u.data_ptr() for s in self.specs)
+            s.holder.weight_u.data_ptr() for s in self.specs) + (ops.SPLIT,)
 
     def _ensure_table(self):
         sig = self._signature()
         if sig == self._ptr_sig:
             return
+        from . import ops
+        planes = 2 if ops.SPLIT else 1  # split-BF16 mode: the lo plane of a layer's pack follows its hi plane
+        pack = 0
+        for s in self.specs:
+            if s.pack_cin > 0:
+                s.pack_off = pack
+                per = s.rows * s.pack_cin * (1 if s.pack_mode == 1 else s.taps)
+                pack += (planes * per + 63) // 64 * 64
+        self.pack_elems = pack
         tab = (N.SnLayer * self.n)()
         for i, s in enumerate(self.specs):
             h = s.holder
@@ -128,7 +138,7 @@ class SNSet(object):
             L.rows, L.cols, L.taps, L.cin = s.rows, s.cols, s.taps, s.cin
             L.pack_cin, L.pack_mode, L.pack_off, L.stencil_off = s.pack_cin, s.pack_mode, s.pack_off, s.stencil_off
             L.gw_off, L.gw_layout = s.gw_off, s.gw_layout
-            L.grad_off = self.param_offsets[id(h.weight_orig)]
+            L.grad_off = self.param_offsets(h.weight_orig)
         call_nostream("spyr_sn_plan", tab, self.n, C.byref(self.plan))
         for i, s in enumerate(self.specs):
             s.saved_off = tab[i].saved_off
@@ -153,7 +163,7 @@ class SNSet(object):
 
     def backward(self, state, gw_arena, grad_arena):
         """dL/dweight_orig for every layer from dL/d(W/sigma) (gw_arena) into grad_arena."""
-        dots = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        dots = torch.empty(max(int(self.plan.tiles_bwd), 1), dtype=torch.float32, device=self.device)
         call("spyr_sn_backward", self.dev_tab.data_ptr(), self.n, C.byref(self.plan), gw_arena.data_ptr(),
              state.saved.data_ptr(), dots.data_ptr(), grad_arena.data_ptr())
 

@@ -20,10 +20,12 @@ POOL_AFTER = (1, 3, 6, 9, 12)  # positions in CONV_IDX followed by MaxPool2d(2)
 
 
 class VGGPack(object):
-    """BF16 operands of the frozen network (built once per weight version)."""
+    """BF16 operands of the frozen network (built once per weight version and precision mode; split-BF16 mode packs a
+    (hi, lo) plane pair per operand)."""
 
     def __init__(self, vgg16):
         dev = vgg16.features[0].weight.device
+        self.split = ops.SPLIT
         self.w, self.b, self.ch = [], [], []
         for j, idx in enumerate(CONV_IDX):
             conv = vgg16.features[idx]
@@ -35,7 +37,7 @@ class VGGPack(object):
                 pk[:, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
             else:
                 pk = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
-            self.w.append(pk.to(BF16).contiguous())
+            self.w.append(ops.to_act(pk))
             self.b.append(conv.bias.detach().float().contiguous())
             self.ch.append((cin, cout))
         fc6, fc7, fc8 = vgg16.classifier[0], vgg16.classifier[3], vgg16.classifier[6]
@@ -47,7 +49,7 @@ class VGGPack(object):
         self.n8, self.n8_pad = n8, (n8 + 7) // 8 * 8
         w8 = torch.zeros(self.n8_pad, fc8.weight.shape[1], dtype=F32, device=dev)
         w8[:n8] = fc8.weight.detach().float()
-        self.fc_w = [w6.to(BF16).contiguous(), fc7.weight.detach().to(BF16).contiguous(), w8.to(BF16).contiguous()]
+        self.fc_w = [ops.to_act(w6), ops.to_act(fc7.weight.detach()), ops.to_act(w8)]
         self.fc_b = [m.bias.detach().float().contiguous() for m in (fc6, fc7, fc8)]
         self.mean = torch.tensor([0.485, 0.456, 0.406], dtype=F32, device=dev)
         self.invstd = 1.0 / torch.tensor([0.229, 0.224, 0.225], dtype=F32, device=dev)
@@ -59,18 +61,21 @@ def _splits(ktotal, ntiles, mtiles=1):
 
 
 def _fc_forward(x_bf16, w, bias, B, K, O, relu, dev, want_bf16=True):
-    acc = torch.zeros((B, O), dtype=F32, device=dev)
-    ops.conv(B, 1, 1, O, [Src(x_bf16, w, K, 1)], f32_out=acc, splits=_splits(K // 64, (O + 255) // 256))
+    # split-K over the reduction: one FP32 slice per split, summed in split order by the epilogue (no atomics)
+    ns = _splits(K // 64, (O + 255) // 256)
+    acc = torch.empty((ns, B, O), dtype=F32, device=dev)
+    # w may hold more rows than O (fc8: 368 for 365 classes): tell the library where its lo plane really starts
+    ops.conv(B, 1, 1, O, [Src(x_bf16, w, K, 1, w_lo_off=w.numel())], f32_out=acc, splits=ns, f32_store=(ns == 1))
     y = torch.empty((B, O), dtype=F32, device=dev)
-    yb = torch.empty((B, O), dtype=BF16, device=dev) if want_bf16 else None
-    call("spyr_vec_epilogue", acc.data_ptr(), bias.data_ptr(), None, None, 1 if relu else 0, y.data_ptr(),
+    yb = ops.act_empty((B, O), dev) if want_bf16 else None
+    call("spyr_vec_epilogue", acc.data_ptr(), ns, bias.data_ptr(), None, None, 1 if relu else 0, y.data_ptr(),
          yb.data_ptr() if want_bf16 else None, O, B, O)
     return y, yb
 
 
 def _dropout(y, p, rng):
     """Inverted dropout of an FP32 activation; returns (y_dropped FP32, BF16 copy, u8 keep mask)."""
-    out, outb = torch.empty_like(y), torch.empty(y.shape, dtype=BF16, device=y.device)
+    out, outb = torch.empty_like(y), ops.act_empty(y.shape, y.device)
     mask = torch.empty(y.shape, dtype=torch.uint8, device=y.device)
     seed, offset = rng
     call("spyr_dropout_fwd", y.data_ptr(), y.numel(), p, seed, offset, out.data_ptr(), outb.data_ptr(), mask.data_ptr())
@@ -83,7 +88,7 @@ def vgg_forward(pk, img, save, dropout=None):
     dropout = (p, seed, offset) applies nn.Dropout(p) after ReLU(fc6) and ReLU(fc7) (torchvision classifier[2], [5])."""
     B, Ci, H, W = img.shape
     dev = img.device
-    col = torch.empty((B, H, W, 32), dtype=BF16, device=dev)
+    col = ops.act_empty((B, H, W, 32), dev)
     call("spyr_im2col3x3", img.data_ptr(), B, H, W, pk.mean.data_ptr(), pk.invstd.data_ptr(), col.data_ptr())
     acts, pools = [], []
     h, w = H, W
@@ -97,7 +102,7 @@ def vgg_forward(pk, img, save, dropout=None):
             pools.append(x)
             h, w = h // 2, w // 2
     c5 = pk.ch[-1][1]
-    pooled = torch.empty((B, 7, 7, c5), dtype=BF16, device=dev)
+    pooled = ops.act_empty((B, 7, 7, c5), dev)
     call("spyr_adaptive_avgpool_fwd", x.data_ptr(), pooled.data_ptr(), B, h, w, 7, 7, c5)
     K6 = 49 * c5
     y6, y6b = _fc_forward(pooled, pk.fc_w[0], pk.fc_b[0], B, K6, pk.fc_w[0].shape[0], True, dev)
@@ -117,10 +122,21 @@ def vgg_forward(pk, img, save, dropout=None):
 
 
 def _fc_dgrad(g_bf16, w, B, K, O, dev):
-    """g (B,1,1,K) @ W[K][O] -> FP32 (B,O) via the MN-major view of the forward pack."""
-    acc = torch.zeros((B, O), dtype=F32, device=dev)
-    ops.conv(B, 1, 1, O, [Src(g_bf16, w, K, 1, mn=True)], f32_out=acc, splits=_splits(K // 64, (O + 255) // 256))
-    return acc
+    """g (B,1,1,K) @ W[K][O] -> FP32 split-K slices (ns,B,O) via the MN-major view of the forward pack; returns
+    (slices, ns) for spyr_vec_epilogue / _sum_slices."""
+    ns = _splits(K // 64, (O + 255) // 256)
+    acc = torch.empty((ns, B, O), dtype=F32, device=dev)
+    ops.conv(B, 1, 1, O, [Src(g_bf16, w, K, 1, mn=True)], f32_out=acc, splits=ns, f32_store=(ns == 1))
+    return acc, ns
+
+
+def _sum_slices(acc, ns, B, O, add=None, want_bf16=False):
+    """FP32 sum of the split-K slices in split order (+ add); optionally also as a BF16 map."""
+    out = torch.empty((B, O), dtype=F32, device=acc.device)
+    outb = ops.act_empty((B, O), acc.device) if want_bf16 else None
+    call("spyr_vec_epilogue", acc.data_ptr(), ns, None, add.data_ptr() if add is not None else None, None, 0,
+         out.data_ptr(), outb.data_ptr() if want_bf16 else None, O, B, O)
+    return out, outb
 
 
 def _conv_param_grads(wg, j, x_in, g, B, h, w, cin, cout):
@@ -160,51 +176,53 @@ def vgg_backward(pk, ctx, g_pools, g7, g8, wg=None):
     g_pool_in = None  # gradient w.r.t. the (B,h5,w5,c5) input of the adaptive pool
     hp, wp = pools[-1].shape[1], pools[-1].shape[2]
     if g7 is not None or g8 is not None:
-        acc7 = None
+        acc7 = None  # FP32 (B, n7): d/d(ReLU(fc7)) = W8^T g8 (+ g7)
+        g7c = g7.contiguous().float() if g7 is not None else None
         if g8 is not None:
-            g8b = torch.zeros((B, pk.n8_pad), dtype=BF16, device=dev)
-            call("spyr_vec_epilogue", g8.contiguous().data_ptr(), None, None, None, 0, None, g8b.data_ptr(), pk.n8_pad, B,
+            g8b = ops.act_zeros((B, pk.n8_pad), dev)
+            call("spyr_vec_epilogue", g8.contiguous().data_ptr(), 1, None, None, None, 0, None, g8b.data_ptr(), pk.n8_pad, B,
                  pk.n8)
-            acc7 = _fc_dgrad(g8b, pk.fc_w[2], B, pk.n8_pad, n7, dev)
-        if acc7 is None:
-            acc7 = g7.contiguous()
-            add7 = None
+            sl7, ns7 = _fc_dgrad(g8b, pk.fc_w[2], B, pk.n8_pad, n7, dev)
+            acc7, _ = _sum_slices(sl7, ns7, B, n7, add=g7c)
         else:
-            add7 = g7.contiguous() if g7 is not None else None
+            acc7 = g7c
         if wg is not None and g8 is not None:
             _fc_param_grads(wg, 2, g8.contiguous(), drop[4] if drop is not None else y7)
         if drop is not None:
             # through the dropout that follows ReLU(fc7): d/dy7 = d/dx8 * mask / (1 - p)
-            acc7 = acc7 + add7 if add7 is not None else (acc7.clone() if g8 is None else acc7)
-            add7 = None
+            if g8 is None:
+                acc7 = acc7.clone()
             call("spyr_dropout_bwd", acc7.data_ptr(), drop[2].data_ptr(), acc7.numel(), drop[0], acc7.data_ptr())
-        g7b = torch.empty((B, n7), dtype=BF16, device=dev)
+        g7b = ops.act_empty((B, n7), dev)
         g7f = torch.empty((B, n7), dtype=F32, device=dev) if wg is not None else None
-        call("spyr_vec_epilogue", acc7.data_ptr(), None, add7.data_ptr() if add7 is not None else None, y7.data_ptr(), 2,
+        call("spyr_vec_epilogue", acc7.data_ptr(), 1, None, None, y7.data_ptr(), 2,
              g7f.data_ptr() if g7f is not None else None, g7b.data_ptr(), n7, B, n7)
         if wg is not None:
             _fc_param_grads(wg, 1, g7f, drop[3] if drop is not None else y6)
-        acc6 = _fc_dgrad(g7b, pk.fc_w[1], B, n7, n6, dev)
+        sl6, ns6 = _fc_dgrad(g7b, pk.fc_w[1], B, n7, n6, dev)
         if drop is not None:
+            acc6, _ = _sum_slices(sl6, ns6, B, n6)
             call("spyr_dropout_bwd", acc6.data_ptr(), drop[1].data_ptr(), acc6.numel(), drop[0], acc6.data_ptr())
-        g6b = torch.empty((B, n6), dtype=BF16, device=dev)
+            sl6, ns6 = acc6, 1
+        g6b = ops.act_empty((B, n6), dev)
         g6f = torch.empty((B, n6), dtype=F32, device=dev) if wg is not None else None
-        call("spyr_vec_epilogue", acc6.data_ptr(), None, None, y6.data_ptr(), 2, g6f.data_ptr() if g6f is not None else None,
-             g6b.data_ptr(), n6, B, n6)
+        call("spyr_vec_epilogue", sl6.data_ptr(), ns6, None, None, y6.data_ptr(), 2,
+             g6f.data_ptr() if g6f is not None else None, g6b.data_ptr(), n6, B, n6)
         if wg is not None:
             # fc6 reads torch's (C,7,7) flattening: present the pooled map in that order so the gradient lands in the
             # parameter's own layout
             x6 = ops.nhwc_to_nchw(pooled).view(B, -1)
             _fc_param_grads(wg, 0, g6f, x6)
-        accp = _fc_dgrad(g6b, pk.fc_w[0], B, n6, 49 * c5, dev)
-        g_pooled = ops.cast_bf16(accp).view(B, 7, 7, c5)
-        g_pool_in = torch.empty((B, hp, wp, c5), dtype=BF16, device=dev)
+        slp, nsp = _fc_dgrad(g6b, pk.fc_w[0], B, n6, 49 * c5, dev)
+        _, g_pooled = _sum_slices(slp, nsp, B, 49 * c5, want_bf16=True)
+        g_pooled = g_pooled.view(B, 7, 7, c5)
+        g_pool_in = ops.act_empty((B, hp, wp, c5), dev)
         call("spyr_adaptive_avgpool_bwd", g_pooled.data_ptr(), g_pools[4].data_ptr() if g_pools[4] is not None else None,
              g_pool_in.data_ptr(), B, hp, wp, 7, 7, c5)
     else:
         g_pool_in = g_pools[4]
     if g_pool_in is None:
-        g_pool_in = torch.zeros((B, hp, wp, c5), dtype=BF16, device=dev)
+        g_pool_in = ops.act_zeros((B, hp, wp, c5), dev)
     # walk the conv stack backwards; g = gradient w.r.t. the output of the current stage
     g = g_pool_in
     level = 4

@@ -32,7 +32,12 @@ def digest(tensors):
     return h.hexdigest()
 
 
-def golden_step():
+def _head(named_parameters, n=256):
+    """First n entries of every gradient tensor: element-level pins (norms alone cannot see a wrong direction)."""
+    return {k: p.grad.flatten()[:n].clone() for k, p in named_parameters if p.grad is not None}
+
+
+def golden_step(CF=CF):
     models, lossfunction, _ = reference_shims.import_reference()
     g_sd, d_sd, v_sd = (O.init_generator_state(CF, seed=SEEDS["g"]), O.init_discriminator_state(CF, seed=SEEDS["d"]),
                         O.init_vgg_state(SEEDS["v"]))
@@ -56,6 +61,8 @@ def golden_step():
     (l_real + l_fake).backward()
     d_grad_norms = {k: float(p.grad.norm()) for k, p in d.named_parameters()}
     d_grad_head = {k: p.grad.flatten()[:64].clone() for k, p in d.named_parameters() if k.endswith("main_block.3.weight_orig")}
+    d_grad_sub = _head(d.named_parameters())
+    prediction_fake_d = prediction_fake.detach().clone()
     d_opt.step()
     g.zero_grad(); d.zero_grad()
     images_fake = g(input=z_g, features=features_real, masks=masks, class_id=labels.float())
@@ -66,6 +73,7 @@ def golden_step():
     l_rec = 0.1 * lossfunction.SemanticReconstructionLoss()(features_real, features_fake, masks)
     (l_g + l_rec + l_div).backward()
     g_grad_norms = {k: float(p.grad.norm()) for k, p in g.named_parameters()}
+    g_grad_sub = _head(g.named_parameters())
     g_opt.step()
     gsd, dsd = g.state_dict(), d.state_dict()
     return {
@@ -79,7 +87,9 @@ def golden_step():
         "images_fake_norm": float(images_fake.norm()),
         "prediction_real": prediction_real.detach().clone(),
         "prediction_fake_g": prediction_fake_g.detach().clone(),
+        "prediction_fake_d": prediction_fake_d,
         "d_grad_norms": d_grad_norms, "g_grad_norms": g_grad_norms, "d_grad_head": d_grad_head,
+        "d_grad_sub": d_grad_sub, "g_grad_sub": g_grad_sub,
         "post_step": {k: gsd[k].clone() for k in ("linear_layer.weight_u", "main_path.2.main_block.3.weight_v",
                                                   "main_path.0.main_block.0.batch_norm.running_mean",
                                                   "final_block.1.running_var", "final_block.1.num_batches_tracked")},
@@ -106,7 +116,9 @@ def golden_masks():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    torch.save(golden_step(), os.path.join(HERE, "step_cf2_b2.pt"))
+    torch.save(golden_step(2), os.path.join(HERE, "step_cf2_b2.pt"))
+    torch.manual_seed(0)
+    torch.save(golden_step(1), os.path.join(HERE, "step_cf1_b2.pt"))  # BASELINE.json configs[0]: cf=1, batch 2
     torch.save(golden_masks(), os.path.join(HERE, "masks.pt"))
-    for name in ("step_cf2_b2.pt", "masks.pt"):
+    for name in ("step_cf2_b2.pt", "step_cf1_b2.pt", "masks.pt"):
         print(name, os.path.getsize(os.path.join(HERE, name)), "bytes")

@@ -1,8 +1,8 @@
 // Debug probe (not on the product path): checks that a 3x3 convolution can be driven from ONE halo tile in shared
 // memory, i.e. that tcgen05.mma accepts A descriptors whose start address is an arbitrary 128-byte row of a
 // SWIZZLE_128B tile written by TMA and whose 8-row groups are (TW+2)*128 bytes apart.
-#include "common.cuh"
-#include "../../include/spyramid_b200.h"
+#include "../../semantic_pyramid_for_image_generation_b200/csrc/common.cuh"
+#include "../../include/spyramid_b200.h"  // (relative to tests/native)
 
 namespace {
 

@@ -143,7 +143,7 @@ static int test_fprop(int B, int H, int W, int Cin, int Cout, int ks, int nsrc, 
   std::vector<float> got(ny), got_act(ny);
   d.block_n = block_n;
   if (splits > 0) {
-    dyf32.alloc(ny * 4);
+    dyf32.alloc(ny * 4 * (size_t)splits);  // one FP32 slice per split (summed in split order by the consumer)
     d.y_f32 = (float*)dyf32.p; d.splits = splits;
   } else {
     dyraw.alloc(ny * 2); d.y_raw = dyraw.p;
@@ -154,7 +154,13 @@ static int test_fprop(int B, int H, int W, int Cin, int Cout, int ks, int nsrc, 
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("  fprop kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
   if (splits > 0) {
-    CK(cudaMemcpy(got.data(), dyf32.p, ny * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> slices(ny * (size_t)splits);
+    CK(cudaMemcpy(slices.data(), dyf32.p, slices.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ny; ++i) {
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += slices[(size_t)sp * ny + i];
+      got[i] = acc;
+    }
   } else {
     std::vector<__nv_bfloat16> gb(ny);
     CK(cudaMemcpy(gb.data(), dyraw.p, ny * 2, cudaMemcpyDeviceToHost));
@@ -206,6 +212,11 @@ static int test_wgrad(int B, int H, int W, int Cin, int Cout, int ks, int lbo, i
   memset(&d, 0, sizeof(d));
   d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = ks;
   d.x = dx.p; d.dy = ddy.p; d.dw = (float*)ddw.p; d.splits = splits; d.dbg_lbo = lbo; d.dbg_sbo = sbo;
+  CK(cudaMemset(ddw.p, 0, ref.size() * 4));
+  Dev dscratch;
+  const long long need = spyr_conv2d_wgrad_scratch_floats(&d);
+  if (need < 0) { printf("  wgrad scratch query: %s\n", spyr_last_error()); return 1; }
+  if (need > 0) { dscratch.alloc((size_t)need * 4); d.scratch = (float*)dscratch.p; d.scratch_floats = need; }
   int rc = spyr_conv2d_wgrad(&d, 0);
   if (rc) { printf("  wgrad rc=%d: %s\n", rc, spyr_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
@@ -328,6 +339,11 @@ static int test_wgrad_per_image(int B, int H, int W, int Cin, int Cout) {
   memset(&d, 0, sizeof(d));
   d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = 1;
   d.x = dx.p; d.dy = ddy.p; d.dw = (float*)ddw.p; d.per_image = 1;
+  CK(cudaMemset(ddw.p, 0, ref.size() * 4));
+  Dev dscratch;
+  const long long need = spyr_conv2d_wgrad_scratch_floats(&d);
+  if (need < 0) { printf("  wgrad scratch query: %s\n", spyr_last_error()); return 1; }
+  if (need > 0) { dscratch.alloc((size_t)need * 4); d.scratch = (float*)dscratch.p; d.scratch_floats = need; }
   int rc = spyr_conv2d_wgrad(&d, 0);
   if (rc) { printf("  wgrad_pi rc=%d: %s\n", rc, spyr_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();

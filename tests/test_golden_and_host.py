@@ -156,7 +156,7 @@ def test_gradient_arena_and_spectral_norm_plan():
     import ctypes as C
     d = models.Discriminator()
     ga, sn = d._ga, d._sn
-    offs = sorted(ga.offsets.values())
+    offs = sorted(ga.offset_list)
     assert offs[0] == 0 and all(o % 64 == 0 for o in offs) and ga.total >= 16820994
     assert sn.n == 28 and sn.gw_floats == sum((s.rows * s.cols + 3) // 4 * 4 for s in sn.specs)
     # first-layer operands are im2col rows; every other conv is [taps][cout][cin]
@@ -174,8 +174,15 @@ def test_gradient_arena_and_spectral_norm_plan():
         tab[i].pack_cin = cin if taps == 9 else 0
     plan = N.SnPlan()
     N.call_nostream("spyr_sn_plan", tab, 2, C.byref(plan))
-    assert plan.tiles_wtu == 1 * 3 + 6 * 1 and plan.tiles_wv == 8 + 46 and plan.tiles_pack == 64 + 1
+    # power iteration: one CTA per 64 columns owning all rows (no cross-CTA sums: deterministic)
+    assert plan.tiles_wtu == 9 + 2 and plan.tiles_wv == 8 + 46 and plan.tiles_pack == 64 + 1
     assert plan.saved_floats == (1 + 64 + 576) + (1 + 365 + 128)
+    # offsets follow the module's CURRENT parameter objects: a deep copy (an EMA generator, say) keeps working
+    import copy
+    d2 = copy.deepcopy(models.Discriminator(channel_factor=4))
+    p_last = list(d2.parameters())[-1]
+    assert d2._ga.offset(p_last) == d2._ga.offset_list[-1] and d2._sn.n == 28
+    assert d2._sn.param_offsets(d2.classification.weight_orig) == d2._ga.offset(d2.classification.weight_orig)
     tab[0].cols = 7  # inconsistent shape -> error status + message, no crash
     with pytest.raises(RuntimeError, match="bad shape"):
         N.call_nostream("spyr_sn_plan", tab, 2, C.byref(plan))
@@ -229,22 +236,42 @@ def _gloo_worker(rank, world, port, out_dir):
     red = distributed.init_from_env("gloo")
     assert red.active and red.world == world and red.rank == rank
 
+    from semantic_pyramid_for_image_generation_b200.engine import GradArena
+
     class M(torch.nn.Module):
         def __init__(self):
             super().__init__()
             self.w = torch.nn.Parameter(torch.zeros(1000))
+            self.b = torch.nn.Parameter(torch.zeros(200003))  # ragged against the bucket size
+            self._ga = GradArena(self)
             self._last_grad_arena = None
 
     m = M()
-    flat = torch.full((200003,), float(rank + 1))  # ragged against the bucket size
     red.bucket_bytes = 1 << 18
-    m._last_grad_arena = flat
+    # (1) gradients that ARE views of the flat arena (what a backward from set_to_none gradients leaves): one bucketed
+    # all-reduce sequence over the arena
+    arena = torch.full((m._ga.total,), float(rank + 1))
+    m._last_grad_arena = arena
+    m.w.grad, m.b.grad = m._ga.views(arena, [True, True])
+    assert red.grads_alias_arena(m, arena)
     red.average(m)
-    assert torch.allclose(flat, torch.full_like(flat, (1 + world) / 2.0))
-    m._last_grad_arena = None
+    assert torch.allclose(arena, torch.full_like(arena, (1 + world) / 2.0))
+    assert torch.allclose(m.b.grad, torch.full_like(m.b.grad, (1 + world) / 2.0))
+    # (2) gradients that do NOT alias the arena (zero_grad(set_to_none=False), accumulation, hooks): the arena is a dead
+    # buffer -- it must be ignored and every .grad averaged on its own (silent divergence otherwise)
     m.w.grad = torch.full((1000,), float(10 * rank))
+    m.b.grad = torch.full((200003,), float(rank))
+    stale = arena.clone()
+    assert not red.grads_alias_arena(m, arena)
     red.average(m)
     assert torch.allclose(m.w.grad, torch.full((1000,), 10.0 * (world - 1) / 2.0))
+    assert torch.allclose(m.b.grad, torch.full((200003,), (world - 1) / 2.0))
+    assert torch.equal(arena, stale)
+    # (3) rank 0's parameters and buffers reach every rank (replaces DataParallel's per-forward replicate)
+    with torch.no_grad():
+        m.w.fill_(float(rank + 5))
+    red.broadcast_module(m)
+    assert torch.equal(m.w.detach(), torch.full((1000,), 5.0))
     assert red.max_over_ranks(float(rank), device="cpu") == float(world - 1)
     lo, hi = distributed.shard_range(41, rank, world)
     torch.save((lo, hi), os.path.join(out_dir, "shard_%d.pt" % rank))

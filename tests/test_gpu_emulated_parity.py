@@ -152,7 +152,7 @@ def _block_param_check(module, prefix, ref_sd, grad_arena, ga, tol):
         gr = ref_sd[name].grad
         if gr is None or p.numel() < 1024 or float(gr.norm()) < 1e-12:
             continue
-        o = ga.offsets[id(p)]
+        o = ga.offset(p)
         mine = grad_arena[o:o + p.numel()].view(p.shape)
         e = rel_l2(mine, gr)
         if e > worst[1]:

@@ -1,6 +1,8 @@
-"""Kernel-level parity (through the C-ABI) against plain PyTorch FP32 ops evaluated on the CPU, on BF16-representable
-inputs.  Tolerance: rel-L2 <= 5e-3 (north_star) for BF16-output kernels (one output rounding = 2^-9 relative,
-rel-L2 ~1.7e-3), <= 1e-4 for FP32-output kernels.
+"""Kernel-level parity (through the C-ABI) against plain PyTorch FP32 ops evaluated on the CPU, on inputs that are exactly
+representable in the mode under test.  Every test runs in both precision modes:
+  bf16   BF16 operands / one-plane maps: rel-L2 <= 5e-3 (north_star) for BF16-output kernels (one output rounding = 2^-9
+         relative, rel-L2 ~1.7e-3), <= 1e-4 for FP32-output kernels;
+  split  (hi, lo) BF16 plane pairs, three tensor-core products per convolution: rel-L2 <= 1e-4 (measured ~1e-5).
 """
 import math
 
@@ -10,8 +12,25 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL_BF16 = 5e-3
 TOL_F32 = 1e-4
+
+
+@pytest.fixture(autouse=True, params=["bf16", "split"])
+def precision_mode(request):
+    from semantic_pyramid_for_image_generation_b200 import ops as o
+    o.set_precision(request.param)
+    yield request.param
+    o.set_precision("bf16")
+
+
+def _o():
+    from semantic_pyramid_for_image_generation_b200 import ops as o
+    return o
+
+
+def tol16():
+    """Tolerance of a kernel whose output is a BF16 map."""
+    return 1e-4 if _o().SPLIT else 5e-3
 
 
 def rel_l2(a, b):
@@ -20,24 +39,32 @@ def rel_l2(a, b):
 
 
 def q(t):
-    return t.bfloat16().float()
+    """Rounds to what a map of the current mode represents exactly (BF16, or hi + lo)."""
+    hi = t.bfloat16().float()
+    if _o().SPLIT:
+        return hi + (t - hi).bfloat16().float()
+    return hi
 
 
 def gen(seed=0):
     return torch.Generator().manual_seed(seed)
 
 
-def nhwc(t):  # NCHW f32 cpu -> NHWC bf16 cuda
-    return t.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+def nhwc(t):  # NCHW f32 cpu -> NHWC map on the GPU (one BF16 plane, or hi + lo)
+    return _o().to_act(t.permute(0, 2, 3, 1).contiguous().cuda())
 
 
-def nchw(t):  # NHWC cuda -> NCHW f32 cpu
-    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+def nchw(t):  # NHWC map on the GPU -> NCHW f32 cpu
+    return _o().act_value(t).cpu().permute(0, 3, 1, 2).contiguous()
 
 
-def pack(w):  # (Cout,Cin,k,k) -> [taps][Cout][Cin] bf16 cuda
+def pack(w):  # (Cout,Cin,k,k) -> [taps][Cout][Cin] operand on the GPU
     co, ci, k, _ = w.shape
-    return w.permute(2, 3, 0, 1).reshape(k * k, co, ci).contiguous().bfloat16().cuda()
+    return _o().to_act(w.permute(2, 3, 0, 1).reshape(k * k, co, ci).contiguous().cuda())
+
+
+def amap(*shape):  # uninitialised map of the current mode
+    return _o().act_empty(shape, "cuda")
 
 
 @pytest.fixture(scope="module")
@@ -61,10 +88,10 @@ def test_conv_fprop_dgrad_wgrad(ops, shape):
     y_ref.backward(dy)
     xc, wc, dyc = nhwc(x), pack(w), nhwc(dy)
     y, ya = ops.conv(B, H, H, Cout, [ops.Src(xc, wc, Cin, k)], bias=b.cuda(), want_act=True)
-    assert rel_l2(nchw(y), y_ref) < TOL_BF16
-    assert rel_l2(nchw(ya), F.leaky_relu(y_ref, 0.2)) < TOL_BF16
+    assert rel_l2(nchw(y), y_ref) < tol16()
+    assert rel_l2(nchw(ya), F.leaky_relu(y_ref, 0.2)) < tol16()
     gx, _ = ops.conv(B, H, H, Cin, [ops.Src(dyc, wc, Cout, k, mn=True)])
-    assert rel_l2(nchw(gx), xr.grad) < TOL_BF16
+    assert rel_l2(nchw(gx), xr.grad) < tol16()
     dw = torch.zeros(k * k, Cin, Cout, device="cuda")
     ops.wgrad(xc, dyc, dw.data_ptr(), B, H, H, Cin, Cout, k)
     dw_ref = wr.grad.permute(2, 3, 1, 0).reshape(k * k, Cin, Cout)
@@ -97,11 +124,11 @@ def test_conv_fused_sources_stencil_gate_residual(ops):
     y, _ = ops.conv(B, H, H, C, [ops.Src(nhwc(a), pack(w6), C, 3), ops.Src(nhwc(xu), pack(wr), C, 1),
                                  ops.Src(fm, pack(wf[:, :Cf].contiguous()), Cf, 3)],
                     bias=b1.cuda(), bias2=b2.cuda(), bias3=b3.cuda(), stencil_mask=m.cuda(), stencil_w=st.cuda())
-    assert rel_l2(nchw(y), ref) < TOL_BF16
+    assert rel_l2(nchw(y), ref) < tol16()
     # mask-channel weight gradient
     dy = q(torch.randn(B, C, H, H, generator=g))
     dw = torch.zeros(9, Cf + 1, C, device="cuda")
-    o.call("spyr_stencil_wgrad", m.cuda(), nhwc(dy), B, H, H, C, dw.data_ptr(), Cf + 1, Cf)
+    o.stencil_wgrad(m.cuda(), nhwc(dy), B, H, H, C, dw.data_ptr(), Cf + 1, Cf)
     mr = m.clone().requires_grad_(False)
     wm = torch.zeros(C, 1, 3, 3, requires_grad=True)
     (F.conv2d(mr, wm, padding=1) * dy).sum().backward()
@@ -112,7 +139,7 @@ def test_conv_fused_sources_stencil_gate_residual(ops):
     gx, _ = ops.conv(B, H, H, C, [ops.Src(nhwc(dy), pack(w6), C, 3, mn=True)], dmask=nhwc(act), dmask_slope=0.2,
                      residual=nhwc(res))
     gref = F.conv_transpose2d(dy, w6, padding=1) * torch.where(act > 0, 1.0, 0.2) + res
-    assert rel_l2(nchw(gx), gref) < TOL_BF16
+    assert rel_l2(nchw(gx), gref) < tol16()
 
 
 def test_first_layer_im2col_path(ops):
@@ -126,17 +153,18 @@ def test_first_layer_im2col_path(ops):
     w = q(torch.randn(C, 3, 3, 3, generator=g) * 0.2)
     b = torch.randn(C, generator=g)
     xn = ((img - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)).requires_grad_(True)
-    col = torch.empty(B, H, H, 32, dtype=torch.bfloat16, device="cuda")
+    col = amap(B, H, H, 32)
     o.call("spyr_im2col3x3", img.cuda(), B, H, H, mean.cuda(), (1 / std).cuda(),
            col.data_ptr())
     ref_col = F.unfold(q(xn.detach()), 3, padding=1).view(B, 3, 9, H, H).permute(0, 3, 4, 2, 1).reshape(B, H, H, 27)
-    assert rel_l2(col[..., :27], ref_col) < 1e-6 and float(col[..., 27:].float().abs().max()) == 0.0
+    colv = o.act_value(col)
+    assert rel_l2(colv[..., :27], ref_col) < 1e-6 and float(colv[..., 27:].abs().max()) == 0.0
     wp = torch.zeros(C, 32)
     wp[:, :27] = w.permute(0, 2, 3, 1).reshape(C, 27)
-    wp = wp.bfloat16().cuda()
+    wp = o.to_act(wp.cuda())
     y, _ = ops.conv(B, H, H, C, [ops.Src(col, wp, 32, 1)], bias=b.cuda())
     y_ref = F.conv2d(q(xn), w, b, padding=1)
-    assert rel_l2(nchw(y), y_ref) < TOL_BF16
+    assert rel_l2(nchw(y), y_ref) < tol16()
     dy = q(torch.randn(B, C, H, H, generator=g))
     xr = q(xn.detach()).requires_grad_(True)
     wr = w.clone().requires_grad_(True)
@@ -147,14 +175,14 @@ def test_first_layer_im2col_path(ops):
     gcol, _ = ops.conv(B, H, H, 32, [ops.Src(nhwc(dy), wp, C, 1, mn=True)])
     gimg = torch.empty(B, 3, H, H, device="cuda")
     o.call("spyr_col2im3x3", gcol.data_ptr(), B, H, H, (1 / std).cuda(), gimg.data_ptr(), 0)
-    assert rel_l2(gimg, xr.grad / std.view(1, 3, 1, 1)) < TOL_BF16
+    assert rel_l2(gimg, xr.grad / std.view(1, 3, 1, 1)) < tol16()
     # skip path: avgpool(img) padded to 8 channels and its transpose
-    p8 = torch.empty(B, H // 2, H // 2, 8, dtype=torch.bfloat16, device="cuda")
+    p8 = amap(B, H // 2, H // 2, 8)
     o.call("spyr_img_avgpool_pad8", img.cuda(), B, H, H, p8.data_ptr())
-    assert rel_l2(nchw(p8)[:, :3], F.avg_pool2d(img, 2)) < TOL_BF16 and float(p8[..., 3:].float().abs().max()) == 0.0
+    assert rel_l2(nchw(p8)[:, :3], F.avg_pool2d(img, 2)) < tol16() and float(o.act_value(p8)[..., 3:].abs().max()) == 0.0
     g8 = q(torch.randn(B, H // 2, H // 2, 8, generator=g))
     acc = torch.ones(B, 3, H, H, device="cuda")
-    o.call("spyr_img_avgpool_pad8_bwd", g8.bfloat16().cuda(), B, H, H, acc.data_ptr(), 1)
+    o.call("spyr_img_avgpool_pad8_bwd", o.to_act(g8.cuda()), B, H, H, acc.data_ptr(), 1)
     ref = 1.0 + 0.25 * F.interpolate(g8.permute(0, 3, 1, 2)[:, :3], scale_factor=2, mode="nearest")
     assert rel_l2(acc, ref) < 1e-6
 
@@ -191,10 +219,10 @@ def test_batchnorm_act_upsample_forward_backward(ops, mode):
     cnt = B * H * H * (4 if mode == 2 else 1)
     mr = o.bn_finalize(sums, cnt, C, 1e-5, 0.1, rmc, rvc, nbt, True)
     a, xu = o.bn_act(xc, mr, embc.data_ptr(), embc.data_ptr() + 4 * C, 2 * C, clsc, mode, want_xu=(mode == 1))
-    assert rel_l2(nchw(a), a_ref) < TOL_BF16
+    assert rel_l2(nchw(a), a_ref) < tol16()
     assert rel_l2(rmc, rm) < 1e-4 and rel_l2(rvc, rv) < 1e-4 and int(nbt) == 1
     if mode == 1:
-        assert rel_l2(nchw(xu), up(x)) < TOL_BF16
+        assert rel_l2(nchw(xu), up(x)) < tol16()
     # backward
     ga = q(torch.randn(a_ref.shape, generator=g))
     a_ref.backward(ga)
@@ -202,32 +230,34 @@ def test_batchnorm_act_upsample_forward_backward(ops, mode):
     M = torch.empty(2 * C, device="cuda")
     demb = torch.zeros(ncls, 2 * C, device="cuda")
     sp, hp = embc.data_ptr(), embc.data_ptr() + 4 * C
+    scr = o.scratch(2 * C, "cuda")
     if mode == 0:
         gy = nhwc(ga * torch.where(a_ref.detach() > 0, 1.0, 0.2))  # the conv epilogue applies this gate
         o.call("spyr_bn_bwd_reduce", gy.data_ptr(), xc.data_ptr(), mr.data_ptr(), sp, hp, 2 * C, clsc.data_ptr(), 0.2, 0,
-               None, S.data_ptr(), B, H, H, C)
+               None, S.data_ptr(), B, H, H, C, scr.data_ptr())
         gsrc, up_flag = gy, 0
     elif mode == 1:
-        gy = torch.empty_like(xc)
+        gy = o.act_like(xc)
         o.call("spyr_bn_bwd_reduce", nhwc(ga), xc.data_ptr(), mr.data_ptr(), sp, hp, 2 * C, clsc.data_ptr(), 0.2,
-               1, gy.data_ptr(), S.data_ptr(), B, H, H, C)
+               1, gy.data_ptr(), S.data_ptr(), B, H, H, C, scr.data_ptr())
         gsrc, up_flag = gy, 0
     else:
         gy = nhwc(ga * torch.where(a_ref.detach() > 0, 1.0, 0.2))
         o.call("spyr_bn_bwd_reduce", gy.data_ptr(), xc.data_ptr(), mr.data_ptr(), sp, hp, 2 * C, clsc.data_ptr(), 0.2, 3,
-               None, S.data_ptr(), B, H, H, C)
+               None, S.data_ptr(), B, H, H, C, scr.data_ptr())
         gsrc, up_flag = gy, 1
     o.call("spyr_bn_bwd_finalize", S.data_ptr(), B, C, float(cnt), sp, 2 * C, clsc.data_ptr(), M.data_ptr(),
            demb.data_ptr(), demb.data_ptr() + 4 * C)
-    gx = torch.empty_like(gsrc)
+    gx = o.act_like(gsrc)
     o.call("spyr_bn_bwd_apply", gsrc.data_ptr(), xc.data_ptr(), mr.data_ptr(), sp, 2 * C, clsc.data_ptr(), M.data_ptr(), None,
            gx.data_ptr(), B, H, H, C, up_flag)
     if mode == 2:
-        lo = torch.empty_like(xc)
+        lo = o.act_like(xc)
         o.call("spyr_up2_bwd", gx.data_ptr(), lo.data_ptr(), B, H, H, C)
         gx = lo
-    assert rel_l2(nchw(gx), xr.grad) < 8e-3
-    assert rel_l2(demb, er.grad) < 5e-3
+    # bf16 mode: gy is re-read as BF16 by the second pass, two roundings on the path
+    assert rel_l2(nchw(gx), xr.grad) < (1e-4 if o.SPLIT else 8e-3)
+    assert rel_l2(demb, er.grad) < (1e-4 if o.SPLIT else 5e-3)
 
 
 def test_pooling_kernels(ops):
@@ -238,9 +268,9 @@ def test_pooling_kernels(ops):
     r = q(torch.randn(B, C, H // 2, H // 2, generator=g))
     y, ya = o.avgpool2(nhwc(x), residual=nhwc(r), want_act=True)
     ref = F.avg_pool2d(x, 2) + r
-    assert rel_l2(nchw(y), ref) < TOL_BF16 and rel_l2(nchw(ya), F.leaky_relu(q(ref), 0.2)) < TOL_BF16
+    assert rel_l2(nchw(y), ref) < tol16() and rel_l2(nchw(ya), F.leaky_relu(q(ref), 0.2)) < tol16()
     gl = q(torch.randn(B, C, H // 2, H // 2, generator=g))
-    assert rel_l2(nchw(o.avgpool2_bwd(nhwc(gl))), 0.25 * F.interpolate(gl, scale_factor=2, mode="nearest")) < TOL_BF16
+    assert rel_l2(nchw(o.avgpool2_bwd(nhwc(gl))), 0.25 * F.interpolate(gl, scale_factor=2, mode="nearest")) < tol16()
     xr = F.relu(x).requires_grad_(True)
     p = F.max_pool2d(xr, 2)
     p.backward(gl)
@@ -252,19 +282,19 @@ def test_pooling_kernels(ops):
     a7 = F.adaptive_avg_pool2d(x8, (7, 7))
     g7 = q(torch.randn(B, C, 7, 7, generator=g))
     a7.backward(g7)
-    y7 = torch.empty(B, 7, 7, C, dtype=torch.bfloat16, device="cuda")
+    y7 = amap(B, 7, 7, C)
     o.call("spyr_adaptive_avgpool_fwd", nhwc(x8.detach()), y7.data_ptr(), B, 8, 8, 7, 7, C)
-    assert rel_l2(nchw(y7), a7) < TOL_BF16
-    g8 = torch.empty(B, 8, 8, C, dtype=torch.bfloat16, device="cuda")
+    assert rel_l2(nchw(y7), a7) < tol16()
+    g8 = amap(B, 8, 8, C)
     o.call("spyr_adaptive_avgpool_bwd", nhwc(g7), None, g8.data_ptr(), B, 8, 8, 7, 7, C)
-    assert rel_l2(nchw(g8), x8.grad) < TOL_BF16
+    assert rel_l2(nchw(g8), x8.grad) < tol16()
     # bilinear transpose
     gh = q(torch.randn(B, C, 2 * H, 2 * H, generator=g))
     xl = x.clone().requires_grad_(True)
     F.interpolate(xl, scale_factor=2, mode="bilinear", align_corners=True).backward(gh)
-    lo = torch.empty(B, H, H, C, dtype=torch.bfloat16, device="cuda")
+    lo = amap(B, H, H, C)
     o.call("spyr_up2_bwd", nhwc(gh), lo.data_ptr(), B, H, H, C)
-    assert rel_l2(nchw(lo), xl.grad) < TOL_BF16
+    assert rel_l2(nchw(lo), xl.grad) < tol16()
 
 
 def test_spectral_norm_forward_backward(ops):
@@ -285,7 +315,7 @@ def test_spectral_norm_forward_backward(ops):
     m = M().cuda()
     ga = GradArena(m)
     sn = SNSet([LayerSpec("a", m.a, pack_cin=40), LayerSpec("b", m.b), LayerSpec("c", m.c, pack_cin=32, stencil=True),
-                LayerSpec("d", m.d)], ga.offsets)
+                LayerSpec("d", m.d)], ga.offset)
     refs = {}
     for key in "abcd":
         h = getattr(m, key)
@@ -305,11 +335,18 @@ def test_spectral_norm_forward_backward(ops):
         off = sn.by_key[key].saved_off
         assert abs(float(st.saved[off]) - float(sigma)) < 1e-5 * float(sigma)
     wa = refs["a"][0].detach() / refs["a"][3]
-    pa = st.packed[sn.by_key["a"].pack_off:sn.by_key["a"].pack_off + 9 * 96 * 40].view(9, 96, 40)
-    assert rel_l2(pa, wa.permute(2, 3, 0, 1).reshape(9, 96, 40)) < TOL_BF16
+    def packed(key, n):  # value of a layer's packed operand: hi plane (+ lo plane right behind it in split mode)
+        off = sn.by_key[key].pack_off
+        v = st.packed[off:off + n].float()
+        if _o().SPLIT:
+            v = v + st.packed[off + n:off + 2 * n].float()
+        return v
+
+    pa = packed("a", 9 * 96 * 40).view(9, 96, 40)
+    assert rel_l2(pa, wa.permute(2, 3, 0, 1).reshape(9, 96, 40)) < tol16()
     wc = refs["c"][0].detach() / refs["c"][3]
-    pc = st.packed[sn.by_key["c"].pack_off:sn.by_key["c"].pack_off + 9 * 64 * 32].view(9, 64, 32)
-    assert rel_l2(pc, wc[:, :32].permute(2, 3, 0, 1).reshape(9, 64, 32)) < TOL_BF16
+    pc = packed("c", 9 * 64 * 32).view(9, 64, 32)
+    assert rel_l2(pc, wc[:, :32].permute(2, 3, 0, 1).reshape(9, 64, 32)) < tol16()
     sc = st.stencil[sn.by_key["c"].stencil_off:sn.by_key["c"].stencil_off + 640].view(10, 64)
     assert rel_l2(sc[:9], wc[:, 32].reshape(64, 9).t()) < 1e-5 and rel_l2(sc[9], wc[:, 32].sum(dim=(1, 2))) < 1e-5
     # backward: G random, layouts as produced by the wgrad kernel (conv) / linear kernels
@@ -329,7 +366,7 @@ def test_spectral_norm_forward_backward(ops):
     sn.backward(st, gw, grad)
     for key in "abcd":
         h = getattr(m, key)
-        o_ = ga.offsets[id(h.weight_orig)]
+        o_ = ga.offset(h.weight_orig)
         mine = grad[o_:o_ + h.weight_orig.numel()].view(h.weight_orig.shape)
         assert rel_l2(mine, refs[key][0].grad) < 1e-4, key
     # eval mode: no iteration, sigma from the stored vectors
@@ -404,11 +441,12 @@ def test_generator_tail_and_adam(ops):
     o.call("spyr_conv1x1_tanh_fwd", ac.data_ptr(), w.cuda(), sigma.cuda(), b.cuda(),
            img.data_ptr(), B, H * H, C, 3)
     assert rel_l2(img, img_ref) < 1e-5
-    gh = torch.empty_like(ac)
+    gh = o.act_like(ac)
     dw, db = torch.zeros(3, C, device="cuda"), torch.zeros(3, device="cuda")
     o.call("spyr_conv1x1_tanh_bwd", gi.cuda(), img.data_ptr(), ac.data_ptr(), w.cuda(),
-           sigma.cuda(), 0.2, gh.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H * H, C, 3)
-    assert rel_l2(nchw(gh), hr.grad * torch.where(a > 0, 1.0, 0.2)) < TOL_BF16
+           sigma.cuda(), 0.2, gh.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H * H, C, 3,
+           o.scratch(3 * C + 3, "cuda"))
+    assert rel_l2(nchw(gh), hr.grad * torch.where(a > 0, 1.0, 0.2)) < tol16()
     assert rel_l2(dw / sigma.cuda(), wr.grad) < 1e-4
     # Adam against torch.optim.Adam for three steps
     ps = [torch.randn(n, generator=g) for n in (5, 1000, 70001)]
@@ -444,7 +482,7 @@ def test_attention_forward_backward(ops):
     ga = engine.GradArena(net)
     specs = [LayerSpec("att." + n, getattr(net.att, n), pack_cin=getattr(net.att, n).shape[1])
              for n in ("query_convolution", "key_convolution", "value_convolution", "attention_convolution")]
-    sn = SNSet(specs, ga.offsets)
+    sn = SNSet(specs, ga.offset)
     sd = {k[len("att."):] if k.startswith("att.") else k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     sd = {"a." + k: v for k, v in sd.items()}
     g = gen(13)
@@ -460,25 +498,29 @@ def test_attention_forward_backward(ops):
     st = sn.forward(True)
     xc = nhwc(x)
     out, _, ctx = engine.attention_forward(net.att, "att", st, xc, False, True)
-    assert rel_l2(nchw(out), out_ref) < TOL_BF16
+    assert rel_l2(nchw(out), out_ref) < tol16()
     grad = ga.new("cuda")
     gw = torch.zeros(sn.gw_floats, device="cuda")
     gx = engine.attention_backward(net.att, "att", st, sn, ga, gw, grad, ctx, nhwc(go))
     sn.backward(st, gw, grad)
-    assert rel_l2(nchw(gx), xr.grad) < 1e-2
+    assert rel_l2(nchw(gx), xr.grad) < (2e-4 if _o().SPLIT else 1e-2)
     for name, p in net.named_parameters():
         ref = sd["a." + name[len("att."):]].grad
-        o_ = ga.offsets[id(p)]
+        o_ = ga.offset(p)
         mine = grad[o_:o_ + p.numel()].view(p.shape)
         if float(ref.norm()) < 1e-6 * float(sd["a.value_convolution.bias"].grad.norm()):
             continue  # key bias: softmax shift invariance makes this gradient analytically zero
-        assert rel_l2(mine, ref) < 2e-2, name
+        assert rel_l2(mine, ref) < (5e-4 if _o().SPLIT else 2e-2), name
 
 
 @pytest.mark.parametrize("shape", [(3, 32, 32, 32, 128), (2, 16, 32, 16, 64), (2, 16, 16, 8, 64)])
 def test_fused_sagan_attention_forward(ops, shape):
     """One-kernel attention (S = QK^T, softmax over keys, O = PV) against torch on BF16-representable q, k, v."""
     from semantic_pyramid_for_image_generation_b200 import ops as o
+    if o.SPLIT:
+        with pytest.raises(RuntimeError, match="split-BF16"):  # single-plane kernel: refuses instead of losing the lo planes
+            o.call("spyr_sagan_attention_fwd", 0, 0, 0, 0, 0, 1, 128, 32, 64, 64)
+        return
     B, H, W, d, dv = shape
     hw, nk = H * W, (H * W) // 4
     g = gen(17)
@@ -491,8 +533,8 @@ def test_fused_sagan_attention_forward(ops, shape):
     pm = torch.empty(B, hw, nk, dtype=torch.bfloat16, device="cuda")
     o.call("spyr_sagan_attention_fwd", qq.bfloat16().cuda(), kk.bfloat16().cuda(), vv.bfloat16().cuda(), out, pm, B, hw, d,
            nk, dv)
-    assert rel_l2(pm, p_ref) < TOL_BF16
-    assert rel_l2(out, o_ref) < TOL_BF16
+    assert rel_l2(pm, p_ref) < tol16()
+    assert rel_l2(out, o_ref) < tol16()
     assert float((pm.float().sum(-1) - 1).abs().max()) < 2e-2
 
 
@@ -505,10 +547,11 @@ def test_arena_add_and_weight_relayout(ops):
     want = a + b
     call("spyr_add_inplace", a.data_ptr(), b.data_ptr(), a.numel())
     assert torch.equal(a, want)
-    w = torch.randn(9, 128, 64, generator=gen(3)).bfloat16().cuda()  # forward pack [tap][Cout=128][Cin=64]
-    out = torch.empty(9, 64, 128, dtype=torch.bfloat16, device="cuda")
+    wf = q(torch.randn(9, 128, 64, generator=gen(3)))
+    w = _o().to_act(wf.cuda())  # forward pack [tap][Cout=128][Cin=64]
+    out = amap(9, 64, 128)
     call("spyr_weight_transpose_flip", w.data_ptr(), out.data_ptr(), 9, 128, 64)
-    assert torch.equal(out, w.flip(0).transpose(1, 2).contiguous())
+    assert torch.equal(_o().act_value(out).cpu(), wf.flip(0).transpose(1, 2).contiguous())
 
 
 def test_input_gradient_of_64_wide_layer_uses_relaid_weights(ops):
@@ -519,7 +562,7 @@ def test_input_gradient_of_64_wide_layer_uses_relaid_weights(ops):
     w = q(torch.randn(cout_f, cin_f, 3, 3, generator=gen(5)) * 0.05)
     want = F.conv_transpose2d(g, w, padding=1)
     got, _ = ops.conv(B, H, W, cin_f, [ops.Src(nhwc(g), pack(w), cout_f, 3, mn=True)])
-    assert rel_l2(nchw(got), want) < TOL_BF16
+    assert rel_l2(nchw(got), want) < tol16()
 
 
 def test_up2_stats_materialises_the_upsampled_map(ops):
@@ -528,7 +571,7 @@ def test_up2_stats_materialises_the_upsampled_map(ops):
     xu, sums = ops.up2_stats(nhwc(x))
     want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
     assert tuple(xu.shape) == (B, 2 * H, 2 * W, C)
-    assert rel_l2(nchw(xu), want) < TOL_BF16
+    assert rel_l2(nchw(xu), want) < tol16()
     xs = nchw(xu).double()  # the statistics are those of the stored BF16 values
     assert torch.allclose(sums[:C].cpu(), xs.sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
     assert torch.allclose(sums[C:].cpu(), (xs * xs).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-6)
@@ -539,6 +582,9 @@ def test_conv_with_fused_average_pool(ops, shape):
     """pool=True: avgpool2(conv(x) + bias) (+ residual at the pooled resolution), raw and LeakyReLU outputs, on both the
     single-CTA (Cout 64, MN... K-major) and the CTA-pair kernels (models.py:406,415-418,451,465)."""
     B, H, W, cin, cout, with_res = shape
+    if ops.SPLIT:
+        assert not ops.can_pool(H, W, cout)  # the split-BF16 mode keeps the separate pooling kernel
+        return
     assert ops.can_pool(H, W, cout)
     x = q(torch.randn(B, cin, H, W, generator=gen(7)))
     w = q(torch.randn(cout, cin, 3, 3, generator=gen(8)) * 0.05)
@@ -550,14 +596,16 @@ def test_conv_with_fused_average_pool(ops, shape):
     raw, act = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3)], bias=b.cuda(),
                         residual=nhwc(res) if with_res else None, want_raw=True, want_act=True, pool=True)
     assert tuple(raw.shape) == (B, H // 2, W // 2, cout)
-    assert rel_l2(nchw(raw), want) < TOL_BF16
-    assert rel_l2(nchw(act), F.leaky_relu(want, 0.2)) < TOL_BF16
+    assert rel_l2(nchw(raw), want) < tol16()
+    assert rel_l2(nchw(act), F.leaky_relu(want, 0.2)) < tol16()
 
 
 def test_conv_with_pooled_residual(ops):
     """residual_pooled=True: out = gate(conv(x)) + 0.25 * upsample_nearest(residual) -- the average-pooled skip branch's
     gradient joining the main path of a discriminator block without its full-resolution copy."""
     B, H, W, cin, cout = 2, 32, 32, 128, 64
+    if ops.SPLIT:
+        return  # fused only in the single-plane mode (engine falls back to the full-resolution skip gradient)
     x = q(torch.randn(B, cin, H, W, generator=gen(11)))
     w = q(torch.randn(cout, cin, 3, 3, generator=gen(12)) * 0.05)
     gate = q(torch.randn(B, cout, H, W, generator=gen(13)))
@@ -566,4 +614,35 @@ def test_conv_with_pooled_residual(ops):
     want = torch.where(gate > 0, want, 0.2 * want) + 0.25 * F.interpolate(res, scale_factor=2, mode="nearest")
     got, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3)], dmask=nhwc(gate), dmask_slope=0.2,
                       residual=nhwc(res), residual_pooled=True)
-    assert rel_l2(nchw(got), want) < TOL_BF16
+    assert rel_l2(nchw(got), want) < tol16()
+
+
+def test_reductions_are_bit_reproducible(ops):
+    """No floating-point atomics: split-K convolutions, weight gradients, bias column sums, BN statistics and the stencil
+    gradient give bit-identical results on repeated launches (the small-map split-K and every weight gradient used
+    red.global.add before, which made the discriminator's prediction move by 1e-2 from run to run)."""
+    o = ops
+    g = gen(21)
+    B, Cin, Cout, H = 4, 256, 512, 8  # small map: split-K over the reduction
+    x, w, dy = nhwc(q(torch.randn(B, Cin, H, H, generator=g))), pack(q(torch.randn(Cout, Cin, 3, 3, generator=g) * 0.03)), \
+        nhwc(q(torch.randn(B, Cout, H, H, generator=g)))
+    runs = []
+    for _ in range(3):
+        y, _ = o.conv(B, H, H, Cout, [o.Src(x, w, Cin, 3)])
+        dw = torch.zeros(9, Cin, Cout, device="cuda")
+        o.wgrad(x, dy, dw.data_ptr(), B, H, H, Cin, Cout, 3)
+        db = torch.zeros(Cout, device="cuda")
+        o.colsum(dy, Cout, db.data_ptr())
+        runs.append((o.act_value(y).clone(), dw, db))
+    for r in runs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], r))
+    B, C, H = 3, 64, 64  # large map: halo-tiled weight gradient with many pixel splits, BN statistics
+    x, dy = nhwc(q(torch.randn(B, C, H, H, generator=g))), nhwc(q(torch.randn(B, C, H, H, generator=g)))
+    runs = []
+    for _ in range(3):
+        dw = torch.zeros(9, C, C, device="cuda")
+        o.wgrad(x, dy, dw.data_ptr(), B, H, H, C, C, 3)
+        runs.append((dw, o.bn_stats(x).clone()))
+    for r in runs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], r))
+    torch.cuda.synchronize()

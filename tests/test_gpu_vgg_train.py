@@ -113,3 +113,27 @@ def test_training_loop_reduces_loss_and_repacks_weights():
     assert vgg_train.learning_rate_for_epoch(1e-4, 30) == pytest.approx(1e-5)
     p1, p5 = vgg_train.precision_at_k(torch.eye(6, device="cuda"), torch.arange(6, device="cuda"), (1, 5))
     assert float(p1) == 100.0 and float(p5) == 100.0
+
+
+def test_fused_adam_step_reaches_the_packed_operands():
+    """FusedAdam updates parameters through raw pointers, so the BF16 operand cache of VGG16 (keyed by
+    parameter versions) must see the update.  With the biases frozen only the WEIGHTS can change the logits."""
+    from semantic_pyramid_for_image_generation_b200.optim import FusedAdam
+    sd = O.init_vgg_state(seed=6)
+    model = _model(sd, train_mode=False)  # eval(): no dropout, the logits are a function of the weights alone
+    for name, p in model.named_parameters():
+        p.requires_grad_(name.endswith("weight"))
+    optimizer = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    target = torch.randint(0, 365, (4,), generator=g).cuda()
+    logits0 = model(x)
+    torch.nn.functional.cross_entropy(logits0.float(), target).backward()
+    v0 = next(p for p in model.parameters() if p.requires_grad)._version
+    optimizer.step()
+    assert next(p for p in model.parameters() if p.requires_grad)._version > v0
+    with torch.no_grad():
+        logits1 = model(x)
+    change = float((logits1.float() - logits0.float().detach()).norm() / logits0.float().norm())
+    print("relative logit change after one weights-only Adam step: %.3e" % change)
+    assert change > 1e-3, change
