@@ -1,15 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: one full G+D training step (model_wrapper.py:136-190 of the reference) at 256x256,
-20 images per GPU, channel_factor 1 -- BASELINE.json configs[2]/[3].
+"""Benchmark of the hot path (BASELINE.json): the Semantic-Pyramid GAN training step at 256x256.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-graph]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3] [--batch B]
+                  [--channel-factor F] [--precision bf16|split] [--no-graph]
+
+  --config 3 (default)  full G+D training step (model_wrapper.py:136-190 of the reference), 20 images per GPU,
+                        channel_factor 1 -- BASELINE.json configs[2] on one GPU, configs[3] under torchrun (N ranks, NCCL);
+                        `--channel-factor 2 --batch 32` is configs[4]
+  --config 2            VGG-16 feature pyramid + Generator forward only (model_wrapper.py:144-151), configs[1]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); the JSON line is printed by rank 0.
-  value      whole-job images/s, inputs resident in HBM, K steps timed with CUDA events (max over ranks)
-  e2e        the same through ModelWrapper with host (pinned) inputs: H2D of images/labels/masks and D2H of the five
-             losses inside the timed region
-  roofline   tensor-core convolution kernel: algorithmic FLOPs of every launch of one step / their CUDA-event time
-  cpu_baseline  oracle/spyramid_oracle.py (CPU restatement of the reference step) on the host cores, rank 0, N=1
+  value         whole-job images/s, inputs resident in HBM, K steps timed with CUDA events (max over ranks)
+  e2e           the same through the public API with host (pinned) inputs: H2D of images/labels/masks and D2H of the
+                step's result inside the timed region
+  roofline      dominant tensor-core kernel: algorithmic FLOPs of every launch of one step / their CUDA-event time, each
+                launch bracketed alone (phase and leaf streams OFF for that pass, so nothing shares the GPU with the
+                timed kernel); keyed by the real kernel name; `traffic` = DRAM bytes per launch from the committed ncu
+                capture (profiles/r02_dram_traffic.json); `hbm` = the dominant bandwidth-bound pass against the HBM peak
+  cpu_baseline  oracle/spyramid_oracle.py (CPU restatement of the reference step) on the host cores, rank 0, N=1, at the
+                benchmark batch (and at batch 2, the reference's own CPU case)
 `--impl reference` times that CPU path alone with the same metric/config keys.
 """
 import argparse
@@ -29,7 +38,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "G+D train images/sec at 256x256, bs=20/GPU"
-FLOPS_PER_IMAGE = 409.8e9  # algorithmically necessary conv+linear+attention FLOPs per image per step
+METRIC_FWD = "VGG-16 pyramid + Generator forward images/sec at 256x256, bs=20"
+# algorithmically necessary conv+linear+attention FLOPs per image: full step / forward only, by channel factor
+FLOPS_PER_IMAGE = {1.0: 409.8e9, 2.0: 197.6e9, 0.5: 1239e9}
+FLOPS_PER_IMAGE_FWD = {1.0: 65.35e9, 2.0: 47.90e9, 0.5: 129.95e9}
 BATCH = 20
 LR = 1e-5
 
@@ -40,11 +52,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3], help="BASELINE.json configs[] entry (1-based)")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--channel-factor", type=float, default=1.0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "split"],
+                    help="bf16: single-plane BF16 operands (throughput mode); split: hi+lo planes, the strict parity mode")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=None, help="CPU baseline batch (default: the benchmark batch)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the reference arm may spend on timed steps")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch tensor-kernel timings of one step here")
     return ap.parse_args()
 
@@ -56,6 +72,15 @@ def peaks():
             p = json.load(f)
         return dict(source="measured", tflops=p["bf16_tflops_sustained"], tflops_burst=p["bf16_tflops"], hbm=p["hbm_gbs"])
     return dict(source="fallback", tflops=1400.0, tflops_burst=1590.0, hbm=6650.0)
+
+
+def dram_traffic():
+    """DRAM bytes per launch of the tensor kernels, from the committed ncu capture (dram__bytes_read + _write)."""
+    path = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 def host_batch(batch, seed):
@@ -87,7 +112,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -100,7 +125,7 @@ class ClockSampler(object):
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         for line in self.lines:
@@ -115,49 +140,154 @@ class ClockSampler(object):
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        # idle samples (before the first kernel) would drag the median down: keep the upper half
-        sm_sorted = sorted(sm)
-        busy = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # raw samples, no filtering: the sampler runs only while the timed loop does
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step_time(batch, steps, warmup, threads):
-    """Times oracle.train_step (the CPU restatement of the reference's step) -- checker code, used here only as the
-    reported baseline."""
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle/spyramid_oracle.py (checker code) used only as the reported baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_step_times(config, cf, batch, steps, warmup, threads, budget_s):
+    """Seconds per step of the CPU restatement of the reference (full step, or VGG + G forward for config 2): `warmup`
+    untimed steps, then up to `steps` timed ones while the time budget lasts (at least one)."""
     from oracle import spyramid_oracle as O
     torch.set_num_threads(threads)
-    g_sd, d_sd, v_sd = O.init_generator_state(1, seed=0), O.init_discriminator_state(1, seed=1), O.init_vgg_state(seed=2)
+    g_sd, d_sd, v_sd = O.init_generator_state(cf, seed=0), O.init_discriminator_state(cf, seed=1), O.init_vgg_state(seed=2)
     images, labels, masks, z_d, z_g = O.synthetic_batch(batch, seed=0, mask_mode="inference")
     g_opt, d_opt = {}, {}
+
+    def one():
+        if config == 2:
+            with torch.no_grad():
+                feats = O.vgg16_features(v_sd, images)
+                O.generator_forward(g_sd, z_d, feats, masks, labels.float(), training=True)
+        else:
+            O.train_step(g_sd, d_sd, v_sd, images, labels, masks, z_d, z_g, g_opt, d_opt, lr=LR)
+
     times = []
+    spent = 0.0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(g_sd, d_sd, v_sd, images, labels, masks, z_d, z_g, g_opt, d_opt, lr=LR)
+        one()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sum(times) / len(times)
+            spent += dt
+            if spent + dt > budget_s:  # the next step would overrun the budget
+                break
+    return times
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    b = args.cpu_batch
-    sec = cpu_reference_step_time(b, args.steps, max(1, min(args.warmup, 1)), threads)
+    cf = args.channel_factor
+    b = args.cpu_batch or args.batch
+    # one cheap warm-up at batch 2 (thread pools, allocator) when the real batch is expensive
+    if b > 4:
+        cpu_step_times(args.config, cf, 2, 1, 0, threads, 1e9)
+        warm = 0
+    else:
+        warm = max(1, min(args.warmup, 1))
+    times = cpu_step_times(args.config, cf, b, args.steps, warm, threads, args.cpu_budget)
+    sec = sum(times) / len(times)
     value = b / sec
-    sample = "oracle.train_step (CPU FP32 restatement of model_wrapper.py:136-190), batch %d per step, %d timed steps, " \
-             "%d threads" % (b, args.steps, threads)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full G+D training step, channel_factor=1, 256x256, CPU sample batch %d" % b,
-                       "batch_per_step": b},
+    what = "full G+D training step (model_wrapper.py:136-190)" if args.config == 3 else \
+        "VGG-16 pyramid + Generator forward (model_wrapper.py:144-151)"
+    sample = "oracle/spyramid_oracle.py (CPU FP32 restatement of the reference: %s), batch %d per step, %d timed step(s) " \
+             "of the %d requested within a %.0f s budget, %d threads" % (what, b, len(times), args.steps, args.cpu_budget,
+                                                                        threads)
+    line = {"impl": "reference", "metric": METRIC if args.config == 3 else METRIC_FWD, "value": value, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "steps_timed": len(times), "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "%s, channel_factor=%g, batch %d, 256x256, CPU" % (what, cf, b), "batch_per_step": b},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline bookkeeping shared by both configs
+# ------------------------------------------------------------------------------------------------
+def profile_pass(fn, ops):
+    """One eager execution of `fn` with every tensor-core launch (and the dominant bandwidth-bound pass) bracketed by its
+    own CUDA-event pair.  Phase streams and leaf streams are off, so the timed kernel has the GPU to itself."""
+    prev = os.environ.get("SPYR_PHASE_STREAMS")
+    os.environ["SPYR_PHASE_STREAMS"] = "0"
+    ops.PROFILE = []
+    try:
+        # Park the GPU behind a ~0.25 s spin so that the whole eager pass is ENQUEUED before any of it runs: the event
+        # pairs then bracket back-to-back kernels.  (Without it the GPU idles between an event record and the launch
+        # that Python issues ~5-10 us later, and that idle time lands inside every bracket: +20 % on 233 launches.)
+        if hasattr(torch.cuda, "_sleep"):
+            torch.cuda._sleep(int(5e8))
+        fn()
+        torch.cuda.synchronize()
+        prof = ops.PROFILE
+    finally:
+        ops.PROFILE = None
+        if prev is None:
+            os.environ.pop("SPYR_PHASE_STREAMS", None)
+        else:
+            os.environ["SPYR_PHASE_STREAMS"] = prev
+    return prof
+
+
+def roofline_from(prof, pk, dump_path=None):
+    if dump_path:
+        rows = {}
+        for kernel, flops, nbytes, a, b, label in prof:
+            r = rows.setdefault((kernel, label), [0, 0.0, flops, nbytes])
+            r[0] += 1
+            r[1] += a.elapsed_time(b)
+        with open(dump_path, "w") as f:
+            for (kernel, label), (n, ms, flops, nbytes) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                f.write("%-20s %-46s n=%3d total %8.3f ms  avg %7.1f us  %7.1f TFLOP/s  %6.0f GB/s(alg)\n" % (
+                    kernel, label, n, ms, ms / n * 1e3, flops * n / (ms * 1e-3) / 1e12, nbytes * n / (ms * 1e-3) / 1e9))
+    agg = {}
+    for kernel, flops, nbytes, a, b, _label in prof:
+        rec = agg.setdefault(kernel, [0.0, 0.0, 0.0, 0])
+        rec[0] += flops
+        rec[1] += nbytes
+        rec[2] += a.elapsed_time(b) * 1e-3
+        rec[3] += 1
+    traffic = dram_traffic()
+    tensor = {k: v for k, v in agg.items() if v[0] > 0}
+    hbm = {k: v for k, v in agg.items() if v[0] == 0 and v[1] > 0}
+    kernels = {}
+    for kernel, (flops, nbytes, sec, n) in tensor.items():
+        kernels[kernel] = {"launches": n, "tflops": flops / sec / 1e12, "ms_per_step": sec * 1e3,
+                           "avg_launch_us": sec / n * 1e6, "frac_of_peak": flops / sec / 1e12 / pk["tflops"],
+                           "dram_bytes_per_launch": traffic.get(kernel, {}).get("dram_bytes_per_launch")}
+    roofline = None
+    if tensor:
+        dom = max(tensor.items(), key=lambda kv: kv[1][2])[0]
+        flops, nbytes, sec, n = tensor[dom]
+        tot_f = sum(v[0] for v in tensor.values())
+        tot_s = sum(v[2] for v in tensor.values())
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": flops / sec / 1e12, "peak": pk["tflops"],
+                    "unit": "TFLOP/s", "frac": flops / sec / 1e12 / pk["tflops"],
+                    "traffic": traffic.get(dom, {}).get("dram_bytes_per_launch"),
+                    "traffic_source": traffic.get(dom, {}).get("source"),
+                    "algorithmic_flops_per_launch": flops / n, "avg_launch_us": sec / n * 1e6,
+                    "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % pk["source"],
+                    "launches_per_step": n, "kernel_ms_per_step": sec * 1e3,
+                    "how": "sum of algorithmic FLOPs (2*pixels*Cout*Cin*taps) of all launches of this kernel in one eager "
+                           "step / sum of their CUDA-event durations on the launching stream; phase and leaf streams off "
+                           "during this pass, so each event pair brackets one kernel running alone",
+                    "all_tensor_kernels": kernels,
+                    "all_tensor_kernels_frac": tot_f / tot_s / 1e12 / pk["tflops"]}
+        if hbm:
+            hk = max(hbm.items(), key=lambda kv: kv[1][2])[0]
+            _, nbytes, sec, n = hbm[hk]
+            roofline["hbm"] = {"bound": "hbm", "kernel": hk, "achieved": nbytes / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": nbytes / sec / 1e9 / pk["hbm"], "launches_per_step": n, "kernel_ms_per_step": sec * 1e3,
+                               "how": "algorithmic bytes (input read once + outputs written once) / CUDA-event time"}
+    return roofline
 
 
 def main():
@@ -176,6 +306,7 @@ def main():
     from semantic_pyramid_for_image_generation_b200 import _native, distributed, models, ops
     from semantic_pyramid_for_image_generation_b200.model_wrapper import METRICS, ModelWrapper
     from semantic_pyramid_for_image_generation_b200.optim import FusedAdam
+    ops.set_precision(args.precision)
     reducer = distributed.init_from_env("nccl") if world > 1 else distributed.GradientReducer()
 
     torch.manual_seed(0)  # identical replicas on every rank
@@ -196,6 +327,15 @@ def main():
     s_labels = h_labels.to(device)
     s_masks = [m.to(device) for m in h_masks]
     h2d_bytes = h_images.numel() * 4 + h_labels.numel() * 8 + sum(m.numel() * 4 for m in h_masks)
+    pk = peaks()
+    dtype = "bf16" if args.precision == "bf16" else "bf16 hi+lo planes (split), fp32 accumulate"
+
+    if args.config == 2:
+        run_forward_config(args, rank, world, local_rank, device, wrapper, G, V, reducer, s_images, s_labels, s_masks,
+                           h_images, h_labels, h_masks, h2d_bytes, pk, dtype, ops, _native)
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
 
     def eager_step():
         return wrapper.training_step(s_images, s_labels, s_masks)
@@ -234,19 +374,19 @@ def main():
     for _ in range(3):
         step()
     # ---- device-resident timing ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     reducer.barrier()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     reducer.barrier()
     ms_total = reducer.max_over_ranks(e0.elapsed_time(e1), device)
-    clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
@@ -279,71 +419,156 @@ def main():
     e2e_value = B * world / (e2e_ms * 1e-3)
     loss_values = loss_host.tolist()
 
-    # ---- roofline of the dominant kernel: every tensor-core conv launch of one eager step, CUDA-event timed ----
-    pk = peaks()
-    ops.PROFILE = []
-    eager_step()
-    torch.cuda.synchronize()
-    prof = ops.PROFILE
-    ops.PROFILE = None
-    agg = {}
-    if args.dump_profile and rank == 0:
-        rows = {}
-        for kernel, flops, nbytes, a, b, label in prof:
-            r = rows.setdefault((kernel, label), [0, 0.0, flops, nbytes])
-            r[0] += 1
-            r[1] += a.elapsed_time(b)
-        with open(args.dump_profile, "w") as f:
-            for (kernel, label), (n, ms, flops, nbytes) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
-                f.write("%-18s %-46s n=%3d total %8.3f ms  avg %7.1f us  %7.1f TFLOP/s  %6.0f GB/s(alg)\n" % (
-                    kernel, label, n, ms, ms / n * 1e3, flops * n / (ms * 1e-3) / 1e12, nbytes * n / (ms * 1e-3) / 1e9))
-    for kernel, flops, nbytes, a, b, _label in prof:
-        rec = agg.setdefault(kernel, [0.0, 0.0, 0.0, 0])
-        rec[0] += flops
-        rec[1] += nbytes
-        rec[2] += a.elapsed_time(b) * 1e-3
-        rec[3] += 1
-    kernels = {}
-    for kernel, (flops, nbytes, sec, n) in agg.items():
-        kernels[kernel] = {"launches": n, "tflops": flops / sec / 1e12, "ms_per_step": sec * 1e3,
-                           "frac_of_peak": flops / sec / 1e12 / pk["tflops"]}
-    dom = max(agg.items(), key=lambda kv: kv[1][2])[0] if agg else None
-    roofline = None
-    if dom is not None:
-        flops, nbytes, sec, n = agg[dom]
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": flops / sec / 1e12, "peak": pk["tflops"],
-                    "unit": "TFLOP/s", "frac": flops / sec / 1e12 / pk["tflops"], "traffic": None,
-                    "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % pk["source"],
-                    "launches_per_step": n, "kernel_ms_per_step": sec * 1e3,
-                    "how": "sum of algorithmic FLOPs (2*pixels*Cout*Cin*taps) of all launches in one eager step / sum of "
-                           "their CUDA-event durations on the launching stream", "all_tensor_kernels": kernels}
+    # ---- roofline: every tensor-core launch of one eager step, each timed alone ----
+    roofline = roofline_from(profile_pass(eager_step, ops), pk, args.dump_profile if rank == 0 else None)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sec = cpu_reference_step_time(args.cpu_batch, 2, 1, threads)
-        cpu_baseline = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": "oracle.train_step (CPU FP32 restatement of the reference step), batch %d, 2 timed steps "
-                                  "after 1 warm-up" % args.cpu_batch}
+        cb = args.cpu_batch or B
+        cpu_step_times(3, cf, 2, 1, 0, threads, 1e9)  # warm-up at batch 2
+        t_small = cpu_step_times(3, cf, 2, 2, 0, threads, 20.0)
+        t_full = cpu_step_times(3, cf, cb, 2, 0, threads, 25.0)
+        sec = sum(t_full) / len(t_full)
+        cpu_baseline = {"value": cb / sec, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": "oracle.train_step (CPU FP32 restatement of the reference step), batch %d (the benchmark "
+                                  "batch), %d timed step(s) after a batch-2 warm-up" % (cb, len(t_full)),
+                        "batch2": {"value": 2 / (sum(t_small) / len(t_small)), "steps": len(t_small),
+                                   "note": "BASELINE.json configs[0]: the reference's own CPU case"}}
     if rank == 0:
+        fpi = FLOPS_PER_IMAGE.get(cf)
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": "full G+D training step (LSGAN + semantic reconstruction + diversity losses, two "
                                        "Adam updates), channel_factor=%g, batch %d/GPU, 256x256" % (cf, B),
+                           "baseline_config": "configs[4]" if (cf == 2.0 and B == 32) else
+                                              ("configs[3]" if world > 1 else "configs[2]"),
                            "global_batch": B * world, "parallelism": "dp%d" % world, "execution": graph_note,
+                           "precision": args.precision, "deterministic": True,
                            "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4 * len(METRICS)},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "launches_per_step": int(launches_per_step),
-                "model_tflops": FLOPS_PER_IMAGE * B * world / (ms_per_step * 1e-3) / 1e12 if cf == 1.0 else None,
+                "model_tflops": fpi * B * world / (ms_per_step * 1e-3) / 1e12 if fpi else None,
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "losses": dict(zip(METRICS, loss_values))}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def run_forward_config(args, rank, world, local_rank, device, wrapper, G, V, reducer, s_images, s_labels, s_masks,
+                       h_images, h_labels, h_masks, h2d_bytes, pk, dtype, ops, _native):
+    """BASELINE.json configs[1]: VGG-16 feature-pyramid extraction + Generator forward only (model_wrapper.py:144-151)."""
+    B = args.batch
+    cf = args.channel_factor
+    labels_f = s_labels.float()
+    z = torch.randn((B, wrapper.latent_dimensions), dtype=torch.float32, device=device)
+
+    def forward():
+        with torch.no_grad():
+            feats = V(s_images)
+            return G(input=z, features=feats, masks=s_masks, class_id=labels_f)
+
+    for _ in range(max(args.warmup, 3)):
+        img = forward()
+    torch.cuda.synchronize()
+    graph, graph_note = None, "eager"
+    _native.launch_count_reset()
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                forward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            _native.launch_count_reset()
+            with torch.cuda.graph(graph):
+                img = forward()
+            graph_note = "cuda-graph (1 per step)"
+        except Exception as exc:  # noqa: BLE001
+            graph, graph_note = None, "eager (graph capture failed: %s)" % str(exc)[:160]
+            torch.cuda.synchronize()
+    if graph is None:
+        _native.launch_count_reset()
+        img = forward()
+        torch.cuda.synchronize()
+    launches_per_step = _native.launch_count()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            forward()
+
+    for _ in range(3):
+        step()
+    reducer.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    reducer.barrier()
+    ms_per_step = reducer.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    # end to end: images / labels / masks from pinned host memory every step, the generated batch's checksum back
+    result_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    reducer.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        s_images.copy_(h_images, non_blocking=True)
+        s_labels.copy_(h_labels, non_blocking=True)
+        for dm, hm in zip(s_masks, h_masks):
+            dm.copy_(hm, non_blocking=True)
+        labels_f.copy_(s_labels)
+        step()
+        result_host.copy_(img.abs().mean().reshape(1), non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    reducer.barrier()
+    e2e_ms = reducer.max_over_ranks(t0.elapsed_time(t1), device) / args.steps
+    roofline = roofline_from(profile_pass(forward, ops), pk, args.dump_profile if rank == 0 else None)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = args.cpu_batch or B
+        cpu_step_times(2, cf, 2, 1, 0, threads, 1e9)
+        t_full = cpu_step_times(2, cf, cb, 3, 0, threads, 25.0)
+        sec = sum(t_full) / len(t_full)
+        cpu_baseline = {"value": cb / sec, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": "oracle VGG-16 pyramid + generator forward (CPU FP32 restatement of the reference), batch "
+                                  "%d, %d timed pass(es) after a batch-2 warm-up" % (cb, len(t_full))}
+    if rank == 0:
+        fpi = FLOPS_PER_IMAGE_FWD.get(cf)
+        line = {"metric": METRIC_FWD, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": "VGG-16 feature pyramid + Generator forward only (model_wrapper.py:144-151), "
+                                       "channel_factor=%g, batch %d/GPU, 256x256" % (cf, B),
+                           "baseline_config": "configs[1]", "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "execution": graph_note, "precision": args.precision, "deterministic": True,
+                           "l2_policy": "per-step working set (>1 GB of activations) exceeds the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
+                "model_tflops": fpi * B * world / (ms_per_step * 1e-3) / 1e12 if fpi else None,
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "result_checksum": float(result_host[0])}
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -41,8 +41,12 @@ int spyr_get_precision(void);
 /* scratch a deterministic reduction over `n_outputs` values needs (partial vectors of up to 296 blocks, 8-byte slots) */
 #define SPYR_REDUCE_BLOCKS 296
 #define SPYR_REDUCE_SCRATCH_BYTES(n_outputs) ((long long)SPYR_REDUCE_BLOCKS * (long long)(n_outputs) * 8)
+/* partial sums of the batch-norm backward: up to 4 * 296 blocks, each (sum gy, sum gy * xhat) for C channels in FP32 */
+#define SPYR_BN_BWD_PARTIAL_BYTES(C) ((long long)(4 * SPYR_REDUCE_BLOCKS + 4 * SPYR_REDUCE_BLOCKS) * 2 * (long long)(C) * 4)
 /* number of kernels launched through this library by the calling process (bench.py "gpu_launches") */
 long long spyr_launch_count(void);
+/* name of the tensor-core kernel the calling thread's last spyr_conv2d_fprop / spyr_conv2d_wgrad launched */
+const char* spyr_last_conv_kernel(void);
 void spyr_launch_count_reset(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -224,20 +228,24 @@ int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const void* a, co
  * Affine convention: scale = scale_ptr[row*row_stride + c], shift = shift_ptr[row*row_stride + c], row = cls[b] or 0.
  * mode 0: a = lrelu(aff(x));  mode 1: a = up2(lrelu(aff(x))), xu = up2(x);  mode 2: a = lrelu(aff(up2(x))).
  * ------------------------------------------------------------------------------------------------ */
-int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums /* [2C] */,
-                  void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C) */, void* stream);
+/* Statistics are deterministic two-stage sums: spyr_bn_stats writes one partial vector (sum, sum of squares; FP64) per
+ * block into `partials` (SPYR_REDUCE_SCRATCH_BYTES(2 * C) bytes) and spyr_bn_finalize adds them in block order. */
+int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* partials, void* stream);
 /* final block (models.py:52-54, upsample -> BN): writes xu = up2(x) (bf16 [B,2H,2W,C]) once and its statistics;
  * sums may be NULL (plain bilinear x2, align_corners=True: the skip branch of a generator block, models.py:338) */
-int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums /* [2C] */,
-                   void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C); may be NULL with sums */, void* stream);
-int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* partials /* may be NULL */,
+                   void* stream);
+int spyr_bn_finalize(const double* partials /* of spyr_bn_stats over `count` pixels; NULL in eval mode */, double count,
+                     int C, float eps, float momentum, float* running_mean,
                      float* running_var, long long* num_batches_tracked, float* mean_rstd /* [2C] */, int training,
                      void* stream);
 int spyr_bn_act(const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr, int row_stride,
                 const int* cls, float slope, int mode, void* out_a, void* out_xu, int B, int H, int W, int C, void* stream);
 int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr, const float* shift_ptr,
-                       int row_stride, const int* cls, float slope, int mode, void* gy_out, float* S /* [B][2][C] */, int B,
-                       int H, int W, int C, void* scratch /* SPYR_REDUCE_SCRATCH_BYTES(2 * C) */, void* stream);
+                       int row_stride, const int* cls, float slope, int mode, void* gy_out,
+                       float* S /* out: [B][2][C] sums, followed by the block partials they are added from (fixed order);
+                                   SPYR_BN_BWD_PARTIAL_BYTES(C) bytes in all */,
+                       int B, int H, int W, int C, void* stream);
 int spyr_bn_bwd_finalize(const float* S, int B, int C, float count, const float* scale_ptr, int row_stride, const int* cls,
                          float* M /* [2C] */, float* d_scale, float* d_shift, void* stream);
 int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mean_rstd, const float* scale_ptr, int row_stride,
@@ -266,11 +274,12 @@ typedef struct {
   int gw_layout;         /* 0: same layout as w;  1: [tap][cin][rows] (spyr_conv2d_wgrad order) */
   long long grad_off;    /* backward: float offset of dL/dweight_orig in grad_arena (layout of w) */
   /* filled by spyr_sn_plan: */
-  int index, tile0_wtu, tile0_wv, tile0_pack, tile0_bwd;
+  int index, tile0_wtu, tile0_wv, tile0_pack, tile0_bwd, tile0_tsum;
   long long scratch_off, saved_off; /* saved arena per layer: sigma, u[rows], v[cols] (the clones torch keeps) */
+  long long part_off;               /* scratch: row-tile partial sums of W^T u (added in tile order: no atomics) */
 } spyr_sn_layer;
 typedef struct {
-  int tiles_wtu, tiles_wv, tiles_pack, tiles_bwd;
+  int tiles_wtu, tiles_wv, tiles_pack, tiles_bwd, tiles_tsum;
   long long scratch_floats, saved_floats;
 } spyr_sn_plan_out;
 int spyr_sn_plan(spyr_sn_layer* host_tab, int n, spyr_sn_plan_out* out); /* host only; fills the planning fields */

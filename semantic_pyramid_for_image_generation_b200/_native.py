@@ -38,13 +38,13 @@ class SnLayer(C.Structure):
     _fields_ = [("w", c_void_p), ("u", c_void_p), ("v", c_void_p), ("rows", c_int), ("cols", c_int), ("taps", c_int),
                 ("cin", c_int), ("pack_cin", c_int), ("pack_mode", c_int), ("pack_off", c_ll), ("stencil_off", c_ll),
                 ("gw_off", c_ll), ("gw_layout", c_int), ("grad_off", c_ll), ("index", c_int), ("tile0_wtu", c_int),
-                ("tile0_wv", c_int), ("tile0_pack", c_int), ("tile0_bwd", c_int), ("scratch_off", c_ll),
-                ("saved_off", c_ll)]
+                ("tile0_wv", c_int), ("tile0_pack", c_int), ("tile0_bwd", c_int), ("tile0_tsum", c_int),
+                ("scratch_off", c_ll), ("saved_off", c_ll), ("part_off", c_ll)]
 
 
 class SnPlan(C.Structure):
     _fields_ = [("tiles_wtu", c_int), ("tiles_wv", c_int), ("tiles_pack", c_int), ("tiles_bwd", c_int),
-                ("scratch_floats", c_ll), ("saved_floats", c_ll)]
+                ("tiles_tsum", c_int), ("scratch_floats", c_ll), ("saved_floats", c_ll)]
 
 
 ADAM_MAX_TENSORS = 48
@@ -84,11 +84,11 @@ _SIGNATURES = {
     "spyr_vec_epilogue": [P, c_int, P, P, P, c_int, P, P, c_int, c_int, c_int, P],
     "spyr_conv1x1_tanh_fwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_conv1x1_tanh_bwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P, P],
-    "spyr_bn_stats": [P, c_int, c_int, c_int, c_int, c_int, P, P, P],
-    "spyr_up2_stats": [P, c_int, c_int, c_int, c_int, P, P, P, P],
+    "spyr_bn_stats": [P, c_int, c_int, c_int, c_int, c_int, P, P],
+    "spyr_up2_stats": [P, c_int, c_int, c_int, c_int, P, P, P],
     "spyr_bn_finalize": [P, c_double, c_int, c_float, c_float, P, P, P, P, c_int, P],
     "spyr_bn_act": [P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
-    "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P, P],
+    "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_bn_bwd_finalize": [P, c_int, c_int, c_float, P, c_int, P, P, P, P, P],
     "spyr_bn_bwd_apply": [P, P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],  # B,H,W,C,x_up2
     "spyr_up2_bwd": [P, P, c_int, c_int, c_int, c_int, P],
@@ -124,7 +124,7 @@ _SIGNATURES = {
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["spyr_last_error", "spyr_version", "spyr_launch_count",
                                                "spyr_launch_count_reset", "spyr_set_precision", "spyr_get_precision",
-                                               "spyr_conv2d_wgrad_scratch_floats"])
+                                               "spyr_conv2d_wgrad_scratch_floats", "spyr_last_conv_kernel"])
 REDUCE_BLOCKS = 296  # SPYR_REDUCE_BLOCKS
 
 _lib = None
@@ -143,6 +143,7 @@ def lib():
         handle.spyr_version.restype = c_int
         handle.spyr_launch_count.restype = c_ll
         handle.spyr_launch_count_reset.restype = None
+        handle.spyr_last_conv_kernel.argtypes, handle.spyr_last_conv_kernel.restype = [], C.c_char_p
         handle.spyr_set_precision.argtypes, handle.spyr_set_precision.restype = [c_int], c_int
         handle.spyr_get_precision.argtypes, handle.spyr_get_precision.restype = [], c_int
         handle.spyr_conv2d_wgrad_scratch_floats.argtypes = [C.POINTER(WgradDesc)]

@@ -18,6 +18,16 @@ void spyr_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static std::atomic<int> g_precision{0};
 bool spyr_split() { return g_precision.load(std::memory_order_relaxed) == 1; }
 
+// which tensor-core kernel the last spyr_conv2d_fprop / spyr_conv2d_wgrad of this thread launched (bench.py keys its
+// roofline entries by the real kernel name)
+static thread_local int g_last_kernel = -1;
+void spyr_note_kernel(int id) { g_last_kernel = id; }
+extern "C" const char* spyr_last_conv_kernel(void) {
+  static const char* names[] = {"conv_halo2_kernel", "conv_halo_kernel", "conv_fprop_kernel", "wgrad_halo_kernel",
+                                "conv_wgrad_kernel"};
+  return (g_last_kernel >= 0 && g_last_kernel < 5) ? names[g_last_kernel] : "";
+}
+
 extern "C" const char* spyr_last_error(void) { return g_err; }
 extern "C" int spyr_set_precision(int mode) {
   SPYR_REQUIRE(mode == 0 || mode == 1, "spyr_set_precision: mode %d (0 = BF16 operands, 1 = split BF16 hi+lo)", mode);

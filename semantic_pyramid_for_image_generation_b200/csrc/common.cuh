@@ -228,18 +228,38 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // ------------------------------------------------------------------------------------------------
 bool spyr_split();  // capi.cu: current precision mode (process-wide)
 
-struct Act {
+// S is the compile-time precision mode of a kernel instantiation: with S = false every lo-plane access is compiled out
+// (as a run-time test on `lo` the extra code cost the bandwidth-bound kernels 10-50 % through registers and code size).
+// Host code builds the generic ActT<true> (`Act`); kernels take ActT<S> and launches go through SPYR_WITH_SPLIT.
+template <bool S>
+struct ActT {
   bf16* p;
-  long long lo;  // elements from the hi plane to the lo plane; 0 = single plane
-  __host__ __device__ __forceinline__ Act operator+(long long off) const { return Act{p + off, lo}; }
-  __host__ __device__ __forceinline__ Act operator+(size_t off) const { return Act{p + off, lo}; }
-  __host__ __device__ __forceinline__ Act operator+(int off) const { return Act{p + off, lo}; }
+  long long lo;  // elements from the hi plane to the lo plane; 0 = single plane (always ignored when S is false)
+  __host__ __device__ __forceinline__ ActT() : p(nullptr), lo(0) {}
+  __host__ __device__ __forceinline__ ActT(bf16* p_, long long lo_) : p(p_), lo(lo_) {}
+  template <bool T>
+  __host__ __device__ __forceinline__ ActT(const ActT<T>& o) : p(o.p), lo(o.lo) {}
+  __host__ __device__ __forceinline__ ActT operator+(long long off) const { return ActT(p + off, lo); }
+  __host__ __device__ __forceinline__ ActT operator+(size_t off) const { return ActT(p + off, lo); }
+  __host__ __device__ __forceinline__ ActT operator+(int off) const { return ActT(p + off, lo); }
   __host__ __device__ __forceinline__ bool null() const { return p == nullptr; }
 };
+typedef ActT<true> Act;
 // host: the map at `ptr` with `n` elements, in the current precision mode
 static inline Act make_act(const void* ptr, long long n) {
-  return Act{reinterpret_cast<bf16*>(const_cast<void*>(ptr)), (ptr != nullptr && spyr_split()) ? n : 0};
+  return Act(reinterpret_cast<bf16*>(const_cast<void*>(ptr)), (ptr != nullptr && spyr_split()) ? n : 0);
 }
+// runs a launch statement with `kS` bound to the current precision mode as a compile-time constant
+#define SPYR_WITH_SPLIT(...)      \
+  do {                            \
+    if (spyr_split()) {           \
+      constexpr bool kS = true;    \
+      __VA_ARGS__;                \
+    } else {                      \
+      constexpr bool kS = false;   \
+      __VA_ARGS__;                \
+    }                             \
+  } while (0)
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -252,18 +272,20 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
 }
 // 8 consecutive channels of a map -> FP32
 __device__ __forceinline__ void ld8(const bf16* p, float* v) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
-__device__ __forceinline__ void ld8(const Act& a, float* v) {
+template <bool S>
+__device__ __forceinline__ void ld8(const ActT<S>& a, float* v) {
   unpack8(*reinterpret_cast<const uint4*>(a.p), v);
-  if (a.lo != 0) {
+  if (S && a.lo != 0) {
     float l[8];
     unpack8(*reinterpret_cast<const uint4*>(a.p + a.lo), l);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += l[j];
   }
 }
-__device__ __forceinline__ void ld8_nc(const Act& a, float* v) {  // read-only path
+template <bool S>
+__device__ __forceinline__ void ld8_nc(const ActT<S>& a, float* v) {  // read-only path
   unpack8(__ldg(reinterpret_cast<const uint4*>(a.p)), v);
-  if (a.lo != 0) {
+  if (S && a.lo != 0) {
     float l[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(a.p + a.lo)), l);
 #pragma unroll
@@ -284,18 +306,20 @@ __device__ __forceinline__ void split_residual8(const float* v, float* lo) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16(v[j]));
 }
-__device__ __forceinline__ void st8(const Act& a, const float* v) {
+template <bool S>
+__device__ __forceinline__ void st8(const ActT<S>& a, const float* v) {
   *reinterpret_cast<uint4*>(a.p) = pack8(v);
-  if (a.lo != 0) {
+  if (S && a.lo != 0) {
     float l[8];
     split_residual8(v, l);
     *reinterpret_cast<uint4*>(a.p + a.lo) = pack8(l);
   }
 }
 // what a later pass reads back from a map written with st8: the stored value (BF16, or hi + lo in split mode)
-__device__ __forceinline__ float stored_value(float v, long long lo) {
+template <bool S>
+__device__ __forceinline__ float stored_value(float v, const ActT<S>& a) {
   const float h = __bfloat162float(__float2bfloat16(v));
-  return lo != 0 ? h + __bfloat162float(__float2bfloat16(v - h)) : h;
+  return (S && a.lo != 0) ? h + __bfloat162float(__float2bfloat16(v - h)) : h;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -305,6 +329,7 @@ __device__ __forceinline__ float stored_value(float v, long long lo) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SPYR_TICKETS = 4096;
 static __device__ unsigned int spyr_ticket_pool[SPYR_TICKETS];
+static __device__ unsigned int spyr_ticket_pool2[SPYR_TICKETS];  // blocks of consecutive tickets (spyr_next_tickets)
 // host: next ticket of this translation unit (round robin; a ticket is busy only while its kernel runs)
 static inline unsigned int* spyr_next_ticket() {
   static unsigned int* base = nullptr;
@@ -315,6 +340,21 @@ static inline unsigned int* spyr_next_ticket() {
     base = reinterpret_cast<unsigned int*>(sym);
   }
   return base + (next++ % SPYR_TICKETS);
+}
+// `n` consecutive tickets (per-sample tails); nullptr when n exceeds the pool
+static inline unsigned int* spyr_next_tickets(int n) {
+  static unsigned int next = 0;
+  if (n > SPYR_TICKETS / 4) return nullptr;
+  static unsigned int* pool = nullptr;
+  if (pool == nullptr) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, spyr_ticket_pool2) != cudaSuccess) return nullptr;
+    pool = reinterpret_cast<unsigned int*>(sym);
+  }
+  if (next + (unsigned)n > (unsigned)SPYR_TICKETS) next = 0;
+  unsigned int* out = pool + next;
+  next += (unsigned)n;
+  return out;
 }
 // true in exactly one block of the grid: the one that arrives last.  Call with all threads of the block after the block's
 // partial results have been written to global memory.
@@ -332,15 +372,17 @@ __device__ __forceinline__ bool spyr_last_block(unsigned int* ticket, unsigned i
   return s_last != 0u;
 }
 // scalar element access of a map (slow path: layout conversions, 3-channel tails)
-__device__ __forceinline__ float ldf(const Act& a, size_t i) {
+template <bool S>
+__device__ __forceinline__ float ldf(const ActT<S>& a, size_t i) {
   float v = __bfloat162float(a.p[i]);
-  if (a.lo != 0) v += __bfloat162float(a.p[i + a.lo]);
+  if (S && a.lo != 0) v += __bfloat162float(a.p[i + a.lo]);
   return v;
 }
-__device__ __forceinline__ void stf(const Act& a, size_t i, float v) {
+template <bool S>
+__device__ __forceinline__ void stf(const ActT<S>& a, size_t i, float v) {
   const bf16 h = __float2bfloat16(v);
   a.p[i] = h;
-  if (a.lo != 0) a.p[i + a.lo] = __float2bfloat16(v - __bfloat162float(h));
+  if (S && a.lo != 0) a.p[i + a.lo] = __float2bfloat16(v - __bfloat162float(h));
 }
 // Tail of a deterministic grid reduction, run by the LAST block only (spyr_last_block): sums the partial vectors
 // scratch[b][n], b in [0, nb), in a fixed order and hands each total to sink(i, total).  blockDim.x / n threads share
@@ -371,6 +413,46 @@ __device__ __forceinline__ void spyr_sum_partials(const T* __restrict__ scratch,
     }
     __syncthreads();
   }
+}
+// Second stage of a deterministic grid reduction as its own (parallel) kernel: one warp per output sums the nb partial
+// vectors scratch[b][n] (lane-strided, then a fixed xor tree) and hands the total to a sink.  Used where n * nb is large
+// (bias column sums, stencil weight gradients): a single last block would serialise ~1M loads.
+//   mode 0: out0[i] += t (+ out1, out2 when given)
+//   mode 1: out0[((i / C) * cin_stride + ci_row) * C + i % C] += t      (mask-channel rows of a strided weight gradient)
+//   mode 2: i < split ? out0[i] += t : out1[i - split] += t
+struct SumSink {
+  float* out0;
+  float* out1;
+  float* out2;
+  int mode, C, cin_stride, ci_row, split;
+};
+__device__ __forceinline__ float spyr_warp_tree(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __global__ void spyr_sum_partials_kernel(const float* __restrict__ scratch, int nb, int n, SumSink sk) {
+  const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = lane; b < nb; b += 32) s += __ldcg(scratch + (size_t)b * n + i);
+  s = spyr_warp_tree(s);
+  if (lane != 0) return;
+  if (sk.mode == 0) {
+    sk.out0[i] += s;
+    if (sk.out1 != nullptr) sk.out1[i] += s;
+    if (sk.out2 != nullptr) sk.out2[i] += s;
+  } else if (sk.mode == 1) {
+    sk.out0[((size_t)(i / sk.C) * sk.cin_stride + sk.ci_row) * sk.C + i % sk.C] += s;
+  } else {
+    if (i < sk.split) sk.out0[i] += s;
+    else sk.out1[i - sk.split] += s;
+  }
+}
+static inline cudaError_t spyr_launch_sum_partials(const float* scratch, int nb, int n, const SumSink& sk, cudaStream_t st) {
+  spyr_sum_partials_kernel<<<(n + 7) / 8, 256, 0, st>>>(scratch, nb, n, sk);
+  return cudaGetLastError();
 }
 // SPYR_REDUCE_BLOCKS (include/spyramid_b200.h) bounds the grid of every reduction kernel, and so its scratch
 

@@ -28,10 +28,12 @@
 #include "conv_halo_common.cuh"
 
 extern void spyr_count_launch();
+void spyr_note_kernel(int id);
 
 namespace {
 using namespace halo;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -311,7 +313,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_dispatch(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
+          epilogue_dispatch<SPLIT>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
@@ -485,7 +487,8 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   SPYR_REQUIRE(smem_bytes <= 227 * 1024, "conv2d_fprop: shared-memory plan of %zu bytes exceeds 227 KB", smem_bytes);
   static bool configured = false;
   if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   static int num_sms = 0;
@@ -495,7 +498,11 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_halo_kernel<<<grid, THREADS, smem_bytes, stream>>>(maps, p);
+  if (p.split)
+    conv_halo_kernel<true><<<grid, THREADS, smem_bytes, stream>>>(maps, p);
+  else
+    conv_halo_kernel<false><<<grid, THREADS, smem_bytes, stream>>>(maps, p);
+  spyr_note_kernel(1);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -22,6 +22,7 @@
 #include "conv_halo_common.cuh"
 
 extern void spyr_count_launch();
+void spyr_note_kernel(int id);
 
 namespace {
 using namespace halo;
@@ -86,6 +87,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -354,7 +356,7 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_dispatch(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
+          epilogue_dispatch<SPLIT>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
@@ -493,7 +495,8 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
                             (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   static int num_sms = 0;
@@ -518,7 +521,11 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel, maps, p));
+  if (p.split)
+    SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel<true>, maps, p));
+  else
+    SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel<false>, maps, p));
+  spyr_note_kernel(0);
   spyr_count_launch();
   return 0;
 }

@@ -19,6 +19,7 @@
 #include "../../include/spyramid_b200.h"
 
 extern void spyr_count_launch();
+void spyr_note_kernel(int id);
 int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream);
 int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream);
 int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream);
@@ -313,16 +314,16 @@ conv_fprop_kernel(const __grid_constant__ TmapPack maps, const FpropParams p) {
           const long long lo = p.split ? p.plane : 0;
           if (p.residual != nullptr) {
             float rv[8];
-            ld8(Act{const_cast<bf16*>(p.residual) + off, lo}, rv);
+            ld8(Act(const_cast<bf16*>(p.residual) + off, lo), rv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += rv[j];
           }
-          if (p.y_raw != nullptr) st8(Act{p.y_raw + off, lo}, v);
+          if (p.y_raw != nullptr) st8(Act(p.y_raw + off, lo), v);
           if (p.y_act != nullptr) {
             const float sl = (p.act == 1) ? 0.f : ((p.act == 2) ? p.act_slope : 1.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-            st8(Act{p.y_act + off, lo}, v);
+            st8(Act(p.y_act + off, lo), v);
           }
         }
       }
@@ -520,28 +521,44 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   }
 }
 
-// dw[img][tap][ci][co] += sum over slices (in slice order) of partial[slice][img][tap][ci][co]; rows ci >= Cin of a
-// strided dw (the mask-channel row of cat(feature*mask, mask)) belong to another kernel and are not touched
+// dw[img][tap][ci][co] += sum over slices of partial[slice][img][tap][ci][co].  `lanes` (a power of two <= 32, chosen from
+// the problem shape only) adjacent threads share one float4 of dw: each adds the slices lane, lane + lanes, ... and a fixed
+// xor tree combines them, so the order of the additions -- and the result, bit for bit -- does not depend on scheduling.
+// Rows ci >= Cin of a strided dw (the mask-channel row of cat(feature*mask, mask)) belong to another kernel: untouched.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nslices, int nimg, float* __restrict__ dw,
-                                    int taps, int Cin, int cin_stride, int Cout) {
+                                    int taps, int Cin, int cin_stride, int Cout, int lanes) {
   const int c4 = Cout >> 2;
   const long long per_img = (long long)taps * Cin * c4;
   const long long total = per_img * nimg;
   const size_t slice_floats = (size_t)taps * cin_stride * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const int lane = (int)(threadIdx.x % (unsigned)lanes);
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const bool live = i < total;  // whole lane groups are live or not: the shuffles below stay within a group
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  size_t off = 0;
+  if (live) {
     const int img = (int)(i / per_img);
     long long r = i - (long long)img * per_img;
     const int co = (int)(r % c4) * 4;
     r /= c4;
     const int ci = (int)(r % Cin), tap = (int)(r / Cin);
-    const size_t off = (size_t)img * slice_floats + ((size_t)tap * cin_stride + ci) * Cout + co;
-    float4 acc = *reinterpret_cast<float4*>(dw + off);
+    off = (size_t)img * slice_floats + ((size_t)tap * cin_stride + ci) * Cout + co;
 #pragma unroll 4
-    for (int sl = 0; sl < nslices; ++sl) {
+    for (int sl = lane; sl < nslices; sl += lanes) {
       const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)sl * nimg * slice_floats + off));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    *reinterpret_cast<float4*>(dw + off) = acc;
+  }
+  for (int o = lanes >> 1; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (live && lane == 0) {
+    float4 d = *reinterpret_cast<float4*>(dw + off);
+    d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
+    *reinterpret_cast<float4*>(dw + off) = d;
   }
 }
 
@@ -725,6 +742,7 @@ static int conv2d_fprop_impl(const spyr_conv_desc* d, cudaStream_t stream) {
   }
   dim3 grid(p.tiles_w * p.tiles_h * tiles_n, ceil_div(d->Cout, bn), p.splits);
   conv_fprop_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
+  spyr_note_kernel(2);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -818,6 +836,7 @@ static int wgrad_tc_launch(const spyr_wgrad_desc* d, const void* x, const void* 
   }
   dim3 grid(ceil_div(p.mchunks, 2), ceil_div(d->Cout, bn), p.splits);
   conv_wgrad_kernel<<<grid, 256, smem_bytes, stream>>>(maps, p);
+  spyr_note_kernel(4);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -878,10 +897,11 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
     const int cs = d->cin_stride > 0 ? d->cin_stride : d->Cin;
     const int rows = cs < d->Cin ? cs : d->Cin;  // operand channels that have a row in dw
     const long long total = (long long)nimg * d->ksize * d->ksize * rows * (d->Cout / 4);
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int lanes = 1;  // threads per output vector: enough parallelism for small gradients with many slices
+    while (lanes < 32 && lanes < slices && total * lanes < 131072) lanes *= 2;
+    const long long blocks = (total * lanes + 255) / 256;
     wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, slices, nimg, d->dw, d->ksize * d->ksize, rows, cs,
-                                                        d->Cout);
+                                                        d->Cout, lanes);
     spyr_count_launch();
     SPYR_LAUNCH_CHECK();
   }

@@ -23,8 +23,9 @@ inline int grid_for(long long n, int block) {
 // ---------------------------------------------------------------------------------------------
 // 3-channel image <-> 32-wide im2col rows (k = tap*3 + c, taps row-major over (dy,dx), 27..31 zero)
 // ---------------------------------------------------------------------------------------------
+template <bool S>
 __global__ void im2col3x3_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ mean,
-                                 const float* __restrict__ invstd, const Act out) {
+                                 const float* __restrict__ invstd, const ActT<S> out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)B * H * W;
   if (idx >= npix) return;
@@ -50,12 +51,13 @@ __global__ void im2col3x3_kernel(const float* __restrict__ img, int B, int H, in
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[t * 3 + c] = in ? (__ldg(base + ((size_t)c * H + hh) * W + ww) - m[c]) * is[c] : 0.f;
   }
-  const Act dst = out + idx * 32;
+  const ActT<S> dst = out + idx * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g) st8(dst + g * 8, v + g * 8);
 }
 
-__global__ void col2im3x3_kernel(const Act gcol, int B, int H, int W, const float* __restrict__ invstd,
+template <bool S>
+__global__ void col2im3x3_kernel(const ActT<S> gcol, int B, int H, int W, const float* __restrict__ invstd,
                                  float* __restrict__ gimg, int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)B * H * W;
@@ -69,7 +71,7 @@ __global__ void col2im3x3_kernel(const Act gcol, int B, int H, int W, const floa
     // col[p][t] = img[p + d_t]  =>  gimg[q] += gcol[q - d_t][t]
     const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const Act src = gcol + ((((size_t)b * H + hh) * W + ww) * 32 + t * 3);
+    const ActT<S> src = gcol + ((((size_t)b * H + hh) * W + ww) * 32 + t * 3);
 #pragma unroll
     for (int c = 0; c < 3; ++c) acc[c] += ldf(src, c);
   }
@@ -83,7 +85,8 @@ __global__ void col2im3x3_kernel(const Act gcol, int B, int H, int W, const floa
 }
 
 // (B,3,H,W) f32 -> 2x2 average -> (B,H/2,W/2,8) bf16 (channels 3..7 zero): input of the D input block's skip conv
-__global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, int H, int W, const Act out) {
+template <bool S>
+__global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, int H, int W, const ActT<S> out) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW) return;
@@ -98,14 +101,15 @@ __global__ void img_avgpool_pad8_kernel(const float* __restrict__ img, int B, in
   }
   st8(out + idx * 8, v);
 }
-__global__ void img_avgpool_pad8_bwd_kernel(const Act g8, int B, int H, int W, float* __restrict__ gimg,
+template <bool S>
+__global__ void img_avgpool_pad8_bwd_kernel(const ActT<S> g8, int B, int H, int W, float* __restrict__ gimg,
                                             int accumulate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W) return;
   const int w = (int)(idx % W);
   const int h = (int)((idx / W) % H);
   const int b = (int)(idx / ((long long)W * H));
-  const Act src = g8 + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * 8;
+  const ActT<S> src = g8 + (((size_t)b * (H / 2) + h / 2) * (W / 2) + w / 2) * 8;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float v = 0.25f * ldf(src, c);
@@ -117,8 +121,9 @@ __global__ void img_avgpool_pad8_bwd_kernel(const Act g8, int B, int H, int W, f
 // ---------------------------------------------------------------------------------------------
 // NCHW f32 <-> NHWC bf16 (API boundary only), optional per-pixel mask gate
 // ---------------------------------------------------------------------------------------------
+template <bool S>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ mask, float slope,
-                                    const Act dst, int C, int HW) {
+                                    const ActT<S> dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -136,7 +141,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, const float* 
     }
   }
 }
-__global__ void nhwc_to_nchw_kernel(const Act src, const float* __restrict__ gate_x, float slope,
+template <bool S>
+__global__ void nhwc_to_nchw_kernel(const ActT<S> src, const float* __restrict__ gate_x, float slope,
                                     float* __restrict__ dst, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -157,7 +163,8 @@ __global__ void nhwc_to_nchw_kernel(const Act src, const float* __restrict__ gat
   }
 }
 
-__global__ void maskgate_kernel(const Act f, const float* __restrict__ mask, const Act out,
+template <bool S>
+__global__ void maskgate_kernel(const ActT<S> f, const float* __restrict__ mask, const ActT<S> out,
                                 long long npix, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix * cg) return;
@@ -173,8 +180,9 @@ __global__ void maskgate_kernel(const Act f, const float* __restrict__ mask, con
 // ---------------------------------------------------------------------------------------------
 // pooling
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool2_fwd_kernel(const Act x, const Act residual, const Act y_raw,
-                                    const Act y_act, float slope, int B, int H, int W, int cg) {
+template <bool S>
+__global__ void avgpool2_fwd_kernel(const ActT<S> x, const ActT<S> residual, const ActT<S> y_raw,
+                                    const ActT<S> y_act, float slope, int B, int H, int W, int cg) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -185,7 +193,7 @@ __global__ void avgpool2_fwd_kernel(const Act x, const Act residual, const Act y
   const int h = (int)(t % OH);
   const int b = (int)(t / OH);
   const size_t C = (size_t)cg * 8;
-  const Act p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
+  const ActT<S> p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
   float a[8], v[8];
   ld8(p, v);
   ld8(p + C, a);
@@ -210,7 +218,8 @@ __global__ void avgpool2_fwd_kernel(const Act x, const Act residual, const Act y
   }
 }
 // g_hi[b,h,w,:] = 0.25 * g_lo[b,h/2,w/2,:]   (H, W are the high-resolution dims)
-__global__ void avgpool2_bwd_kernel(const Act g_lo, const Act g_hi, int B, int H, int W, int cg) {
+template <bool S>
+__global__ void avgpool2_bwd_kernel(const ActT<S> g_lo, const ActT<S> g_hi, int B, int H, int W, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
   const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
@@ -226,7 +235,8 @@ __global__ void avgpool2_bwd_kernel(const Act g_lo, const Act g_hi, int B, int H
   st8(g_hi + idx * 8, v);
 }
 
-__global__ void maxpool2_fwd_kernel(const Act x, const Act y, int B, int H, int W, int cg) {
+template <bool S>
+__global__ void maxpool2_fwd_kernel(const ActT<S> x, const ActT<S> y, int B, int H, int W, int cg) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -237,7 +247,7 @@ __global__ void maxpool2_fwd_kernel(const Act x, const Act y, int B, int H, int 
   const int h = (int)(t % OH);
   const int b = (int)(t / OH);
   const size_t C = (size_t)cg * 8;
-  const Act p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
+  const ActT<S> p = x + ((((size_t)b * H + 2 * h) * W + 2 * w) * C + (size_t)c * 8);
   float a[8], v[8];
   ld8(p, v);
   ld8(p + C, a);
@@ -253,7 +263,8 @@ __global__ void maxpool2_fwd_kernel(const Act x, const Act y, int B, int H, int 
 }
 // routes gy to the FIRST maximum of each 2x2 window in (row, col) scan order (ATen max_pool2d backward),
 // optionally gated by x > 0 (the ReLU that produced x).
-__global__ void maxpool2_bwd_kernel(const Act x, const Act gy, const Act gx, int B,
+template <bool S>
+__global__ void maxpool2_bwd_kernel(const ActT<S> x, const ActT<S> gy, const ActT<S> gx, int B,
                                     int H, int W, int cg, int relu_gate, int accumulate) {
   const int OH = H / 2, OW = W / 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,7 +318,8 @@ __device__ __forceinline__ void adaptive_win(int i, int in, int out, int* s, int
   *s = (i * in) / out;
   *e = ((i + 1) * in + out - 1) / out;
 }
-__global__ void adaptive_avgpool_fwd_kernel(const Act x, const Act y, int B, int H, int W, int OH,
+template <bool S>
+__global__ void adaptive_avgpool_fwd_kernel(const ActT<S> x, const ActT<S> y, int B, int H, int W, int OH,
                                             int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * OH * OW * cg) return;
@@ -332,8 +344,9 @@ __global__ void adaptive_avgpool_fwd_kernel(const Act x, const Act y, int B, int
   for (int j = 0; j < 8; ++j) acc[j] *= inv;
   st8(y + idx * 8, acc);
 }
-__global__ void adaptive_avgpool_bwd_kernel(const Act gy, const Act residual,
-                                            const Act gx, int B, int H, int W, int OH, int OW, int cg) {
+template <bool S>
+__global__ void adaptive_avgpool_bwd_kernel(const ActT<S> gy, const ActT<S> residual,
+                                            const ActT<S> gx, int B, int H, int W, int OH, int OW, int cg) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
   const int c = (int)((unsigned)idx % (unsigned)cg);  // 32-bit index split: element counts are < 2^31 (checked at launch)
@@ -366,7 +379,8 @@ __global__ void adaptive_avgpool_bwd_kernel(const Act gy, const Act residual,
 }
 
 // feat[b][c] = mean_p lrelu(x[b,p,c])  (models.py:125-127); one block per image, threads over channels
-__global__ void global_avgpool_lrelu_fwd_kernel(const Act x, float slope, float* __restrict__ out, int P,
+template <bool S>
+__global__ void global_avgpool_lrelu_fwd_kernel(const ActT<S> x, float slope, float* __restrict__ out, int P,
                                                 int C) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -375,8 +389,9 @@ __global__ void global_avgpool_lrelu_fwd_kernel(const Act x, float slope, float*
     out[(size_t)b * C + c] = acc / (float)P;
   }
 }
-__global__ void global_avgpool_lrelu_bwd_kernel(const Act x, const float* __restrict__ gfeat, float slope,
-                                                const Act gx, int P, int C) {
+template <bool S>
+__global__ void global_avgpool_lrelu_bwd_kernel(const ActT<S> x, const float* __restrict__ gfeat, float slope,
+                                                const ActT<S> gx, int P, int C) {
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < P * C; i += blockDim.x) {
     const int c = i % C;
@@ -389,9 +404,10 @@ __global__ void global_avgpool_lrelu_bwd_kernel(const Act x, const float* __rest
 // ---------------------------------------------------------------------------------------------
 // out = gamma * t + x   and its backward  (SelfAttention tail, models.py:274)
 // ---------------------------------------------------------------------------------------------
-__global__ void gamma_residual_fwd_kernel(const Act t, const Act x,
-                                          const float* __restrict__ gamma, const Act out,
-                                          const Act out_act, float slope, long long n8) {
+template <bool S>
+__global__ void gamma_residual_fwd_kernel(const ActT<S> t, const ActT<S> x,
+                                          const float* __restrict__ gamma, const ActT<S> out,
+                                          const ActT<S> out_act, float slope, long long n8) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n8) return;
   const float g = __ldg(gamma);
@@ -404,13 +420,14 @@ __global__ void gamma_residual_fwd_kernel(const Act t, const Act x,
   if (!out_act.null()) {
     // activate the value the raw output holds (BF16-rounded, or hi + lo in split mode)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = lrelu_f(stored_value(a[j], out.lo), slope);
+    for (int j = 0; j < 8; ++j) a[j] = lrelu_f(stored_value(a[j], out), slope);
     st8(out_act + idx * 8, a);
   }
 }
 // gt = gamma * g ; dgamma += sum(g * t)
-__global__ void gamma_residual_bwd_kernel(const Act g, const Act t,
-                                          const float* __restrict__ gamma, const Act gt,
+template <bool S>
+__global__ void gamma_residual_bwd_kernel(const ActT<S> g, const ActT<S> t,
+                                          const float* __restrict__ gamma, const ActT<S> gt,
                                           float* __restrict__ dgamma, long long n8, float* __restrict__ scratch,
                                           unsigned int* ticket) {
   const float gm = __ldg(gamma);
@@ -440,9 +457,8 @@ __global__ void gamma_residual_bwd_kernel(const Act g, const Act t,
 }
 
 // out_i[c] += sum_rows g[row][c]   (bias gradients; up to three identical destinations)
-__global__ void colsum_kernel(const Act g, long long rows, int cg, float* __restrict__ o0,
-                              float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ scratch,
-                              unsigned int* ticket) {
+template <bool S>
+__global__ void colsum_kernel(const ActT<S> g, long long rows, int cg, float* __restrict__ scratch) {
   extern __shared__ float sh[];  // [prows][cg*8]
   const int c = threadIdx.x % cg;
   const int pr = threadIdx.x / cg;
@@ -466,19 +482,13 @@ __global__ void colsum_kernel(const Act g, long long rows, int cg, float* __rest
     for (int r = 0; r < prows; ++r) s += sh[r * C + i];
     scratch[(size_t)blockIdx.x * C + i] = s;
   }
-  if (spyr_last_block(ticket, gridDim.x))
-    spyr_sum_partials<float>(scratch, (int)gridDim.x, C, [&](int i, float total) {
-      o0[i] += total;
-      if (o1 != nullptr) o1[i] += total;
-      if (o2 != nullptr) o2[i] += total;
-    });
 }
 
 // dw[(t*cin_stride + ci_row)*Cout + co] += sum_{b,h,w} mask[b,h+dy,w+dx] * g[b,h,w,co]
 // (weight gradient of the mask channel of `cat(feature*mask, mask)`, models.py:94,336)
-__global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const Act g, int B, int H, int W,
-                                     int cg, float* __restrict__ dw, int cin_stride, int ci_row,
-                                     float* __restrict__ scratch, unsigned int* ticket) {
+template <bool S>
+__global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const ActT<S> g, int B, int H, int W,
+                                     int cg, float* __restrict__ scratch) {
   extern __shared__ float sh[];  // [prows][9][C]
   const int C = cg * 8;
   const int c = threadIdx.x % cg;
@@ -535,11 +545,6 @@ __global__ void stencil_wgrad_kernel(const float* __restrict__ mask, const Act g
     for (int r = 0; r < prows; ++r) s += sh[r * 9 * C + i];
     scratch[(size_t)blockIdx.x * 9 * C + i] = s;
   }
-  if (spyr_last_block(ticket, gridDim.x))
-    spyr_sum_partials<float>(scratch, (int)gridDim.x, 9 * C, [&](int i, float total) {
-      const int t = i / C, co = i % C;
-      dw[((size_t)t * cin_stride + ci_row) * C + co] += total;
-    });
 }
 
 // dst[t][n][k] = src[taps-1-t][k][n]: the packed forward weights [tap][Cout][Cin] re-laid out as the K-major operand of
@@ -592,8 +597,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
+template <bool S>
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
-                                   unsigned long long offset, float* __restrict__ y, const Act y_bf16,
+                                   unsigned long long offset, float* __restrict__ y, const ActT<S> y_bf16,
                                    unsigned char* __restrict__ mask) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -610,14 +616,16 @@ __global__ void dropout_bwd_kernel(const float* __restrict__ g, const unsigned c
   if (i < n) out[i] = mask[i] ? g[i] / (1.f - p) : 0.f;
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, const Act dst, long long n) {
+template <bool S>
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, const ActT<S> dst, long long n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) stf(dst, (size_t)idx, src[idx]);
 }
 
+template <bool S>
 __global__ void vec_epilogue_kernel(const float* __restrict__ acc, int nsplit, const float* __restrict__ bias,
                                     const float* __restrict__ add, const float* __restrict__ gate, int mode,
-                                    float* __restrict__ out_f32, const Act out_bf16, int ld_bf16, int B, int N) {
+                                    float* __restrict__ out_f32, const ActT<S> out_bf16, int ld_bf16, int B, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * N) return;
   float v = acc[i];
@@ -636,11 +644,12 @@ __global__ void vec_epilogue_kernel(const float* __restrict__ acc, int nsplit, c
 // the same fused tail as the in-kernel epilogue of spyr_conv2d_fprop: biases, mask-channel stencil, gate, residual,
 // raw + activated BF16 outputs.
 // ---------------------------------------------------------------------------------------------
+template <bool S>
 __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int nsplit, int B, int H, int W, int cg,
                                      const float* __restrict__ bias, const float* __restrict__ bias2,
                                      const float* __restrict__ bias3, const float* __restrict__ stencil_mask,
-                                     const float* __restrict__ stencil_w, const Act dmask, float dmask_slope,
-                                     const Act residual, const Act y_raw, const Act y_act,
+                                     const float* __restrict__ stencil_w, const ActT<S> dmask, float dmask_slope,
+                                     const ActT<S> residual, const ActT<S> y_raw, const ActT<S> y_act,
                                      int act, float act_slope) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * cg) return;
@@ -704,8 +713,8 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ acc, int nsplit, 
 // ---------------------------------------------------------------------------------------------
 // generator tail: img = tanh(conv1x1(a; W/sigma) + b), C -> 3 channels, NCHW f32 out  (models.py:58-61,99)
 // ---------------------------------------------------------------------------------------------
-template <int CO>
-__global__ void conv1x1_tanh_fwd_kernel(const Act a, const float* __restrict__ w,
+template <int CO, bool S>
+__global__ void conv1x1_tanh_fwd_kernel(const ActT<S> a, const float* __restrict__ w,
                                         const float* __restrict__ sigma, const float* __restrict__ bias,
                                         float* __restrict__ img, int HW, int C, long long npix) {
   extern __shared__ float ws[];  // [CO][C]
@@ -730,12 +739,11 @@ __global__ void conv1x1_tanh_fwd_kernel(const Act a, const float* __restrict__ w
   for (int o = 0; o < CO; ++o) img[((size_t)b * CO + o) * HW + q] = tanhf(acc[o]);
 }
 // gh[p][k] = (sum_o gpre[o] W[o][k]/sigma) * lrelu'(a[p][k]);  dW_sn[o][k] += sum_p gpre[o] a[p][k];  db[o] += sum_p gpre[o]
-template <int CO>
+template <int CO, bool S>
 __global__ void conv1x1_tanh_bwd_kernel(const float* __restrict__ gimg, const float* __restrict__ img,
-                                        const Act a, const float* __restrict__ w,
-                                        const float* __restrict__ sigma, float slope, const Act gh,
-                                        float* __restrict__ dw, float* __restrict__ db, int HW, int C, long long npix,
-                                        float* __restrict__ scratch, unsigned int* ticket) {
+                                        const ActT<S> a, const float* __restrict__ w,
+                                        const float* __restrict__ sigma, float slope, const ActT<S> gh,
+                                        int HW, int C, long long npix, float* __restrict__ scratch) {
   extern __shared__ float sh[];  // ws[CO][C] then red[prows][CO][C] then redb[prows][CO]
   const int cg = C / 8;
   const int c = threadIdx.x % cg;
@@ -800,11 +808,6 @@ __global__ void conv1x1_tanh_bwd_kernel(const float* __restrict__ gimg, const fl
     for (int r = 0; r < prows; ++r) s += redb[r * CO + threadIdx.x];
     scratch[(size_t)blockIdx.x * (CO * C + CO) + CO * C + threadIdx.x] = s;
   }
-  if (spyr_last_block(ticket, gridDim.x))
-    spyr_sum_partials<float>(scratch, (int)gridDim.x, CO * C + CO, [&](int i, float total) {
-      if (i < CO * C) dw[i] += total;
-      else db[i - CO * C] += total;
-    });
 }
 
 }  // namespace
@@ -815,7 +818,7 @@ extern "C" int spyr_im2col3x3(const float* img, int B, int H, int W, const float
                               void* stream) {
   SPYR_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "im2col3x3: bad arguments");
   const long long n = (long long)B * H * W;
-  im2col3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(img, B, H, W, mean3, invstd3, make_act(out, n * 32));
+  SPYR_WITH_SPLIT(im2col3x3_kernel<kS><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(img, B, H, W, mean3, invstd3, make_act(out, n * 32)));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -824,8 +827,8 @@ extern "C" int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float
                               void* stream) {
   SPYR_REQUIRE(gcol && gimg && B > 0, "col2im3x3: bad arguments");
   const long long n = (long long)B * H * W;
-  col2im3x3_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(make_act(gcol, n * 32), B, H, W, invstd3, gimg,
-                                                                       accumulate);
+  SPYR_WITH_SPLIT(col2im3x3_kernel<kS><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(make_act(gcol, n * 32), B, H, W, invstd3, gimg,
+                                                                       accumulate));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -833,7 +836,7 @@ extern "C" int spyr_col2im3x3(const void* gcol, int B, int H, int W, const float
 extern "C" int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void* out, void* stream) {
   SPYR_REQUIRE(img && out && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8: bad arguments");
   const long long n = (long long)B * (H / 2) * (W / 2);
-  img_avgpool_pad8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, make_act(out, n * 8));
+  SPYR_WITH_SPLIT(img_avgpool_pad8_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, make_act(out, n * 8)));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -841,8 +844,8 @@ extern "C" int spyr_img_avgpool_pad8(const float* img, int B, int H, int W, void
 extern "C" int spyr_img_avgpool_pad8_bwd(const void* g8, int B, int H, int W, float* gimg, int accumulate, void* stream) {
   SPYR_REQUIRE(g8 && gimg && H % 2 == 0 && W % 2 == 0, "img_avgpool_pad8_bwd: bad arguments");
   const long long n = (long long)B * H * W;
-  img_avgpool_pad8_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g8, n * 2), B, H, W, gimg,
-                                                                                  accumulate);
+  SPYR_WITH_SPLIT(img_avgpool_pad8_bwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g8, n * 2), B, H, W, gimg,
+                                                                                  accumulate));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -851,7 +854,7 @@ extern "C" int spyr_nchw_to_nhwc(const float* src, const float* mask, float slop
                                  void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, slope, make_act(dst, (long long)B * C * HW), C, HW);
+  SPYR_WITH_SPLIT(nchw_to_nhwc_kernel<kS><<<grid, block, 0, (cudaStream_t)stream>>>(src, mask, slope, make_act(dst, (long long)B * C * HW), C, HW));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -860,15 +863,15 @@ extern "C" int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slo
                                  void* stream) {
   SPYR_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(make_act(src, (long long)B * C * HW), gate_x, slope, dst, C, HW);
+  SPYR_WITH_SPLIT(nhwc_to_nchw_kernel<kS><<<grid, block, 0, (cudaStream_t)stream>>>(make_act(src, (long long)B * C * HW), gate_x, slope, dst, C, HW));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream) {
   SPYR_C8(C);
-  maskgate_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(make_act(f, npix * C), mask, make_act(out, npix * C), npix,
-                                                                                   C / 8);
+  SPYR_WITH_SPLIT(maskgate_kernel<kS><<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(make_act(f, npix * C), mask, make_act(out, npix * C), npix,
+                                                                                   C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -879,8 +882,8 @@ extern "C" int spyr_avgpool2_fwd(const void* x, const void* residual, void* y_ra
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  avgpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(residual, n * 8),
-                                                                          make_act(y_raw, n * 8), make_act(y_act, n * 8), slope, B, H, W, C / 8);
+  SPYR_WITH_SPLIT(avgpool2_fwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(residual, n * 8),
+                                                                          make_act(y_raw, n * 8), make_act(y_act, n * 8), slope, B, H, W, C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -889,7 +892,7 @@ extern "C" int spyr_avgpool2_bwd(const void* g_lo, void* g_hi, int B, int H, int
   SPYR_C8(C);
   const long long n = (long long)B * H * W * (C / 8);
   SPYR_N32(n);
-  avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g_lo, n * 2), make_act(g_hi, n * 8), B, H, W, C / 8);
+  SPYR_WITH_SPLIT(avgpool2_bwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(g_lo, n * 2), make_act(g_hi, n * 8), B, H, W, C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -899,7 +902,7 @@ extern "C" int spyr_maxpool2_fwd(const void* x, void* y, int B, int H, int W, in
   SPYR_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: odd size");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  maxpool2_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(y, n * 8), B, H, W, C / 8);
+  SPYR_WITH_SPLIT(maxpool2_fwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(y, n * 8), B, H, W, C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -909,8 +912,8 @@ extern "C" int spyr_maxpool2_bwd(const void* x, const void* gy, void* gx, int B,
   SPYR_C8(C);
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
-  maxpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(gy, n * 8), make_act(gx, n * 32), B, H,
-                                                                          W, C / 8, relu_gate, accumulate);
+  SPYR_WITH_SPLIT(maxpool2_bwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, n * 32), make_act(gy, n * 8), make_act(gx, n * 32), B, H,
+                                                                          W, C / 8, relu_gate, accumulate));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -919,8 +922,8 @@ extern "C" int spyr_adaptive_avgpool_fwd(const void* x, void* y, int B, int H, i
   SPYR_C8(C);
   const long long n = (long long)B * OH * OW * (C / 8);
   SPYR_N32(n);
-  adaptive_avgpool_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * H * W * C), make_act(y, n * 8), B, H, W, OH, OW,
-                                                                                  C / 8);
+  SPYR_WITH_SPLIT(adaptive_avgpool_fwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * H * W * C), make_act(y, n * 8), B, H, W, OH, OW,
+                                                                                  C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -930,21 +933,21 @@ extern "C" int spyr_adaptive_avgpool_bwd(const void* gy, const void* residual, v
   SPYR_C8(C);
   const long long n = (long long)B * H * W * (C / 8);
   SPYR_N32(n);
-  adaptive_avgpool_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      make_act(gy, (long long)B * OH * OW * C), make_act(residual, n * 8), make_act(gx, n * 8), B, H, W, OH, OW, C / 8);
+  SPYR_WITH_SPLIT(adaptive_avgpool_bwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      make_act(gy, (long long)B * OH * OW * C), make_act(residual, n * 8), make_act(gx, n * 8), B, H, W, OH, OW, C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_global_avgpool_lrelu_fwd(const void* x, float slope, float* out, int B, int P, int C, void* stream) {
-  global_avgpool_lrelu_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), slope, out, P, C);
+  SPYR_WITH_SPLIT(global_avgpool_lrelu_fwd_kernel<kS><<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), slope, out, P, C));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, float slope, void* gx, int B, int P, int C,
                                              void* stream) {
-  global_avgpool_lrelu_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), gfeat, slope, make_act(gx, (long long)B * P * C), P, C);
+  SPYR_WITH_SPLIT(global_avgpool_lrelu_bwd_kernel<kS><<<B, 256, 0, (cudaStream_t)stream>>>(make_act(x, (long long)B * P * C), gfeat, slope, make_act(gx, (long long)B * P * C), P, C));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -952,8 +955,8 @@ extern "C" int spyr_global_avgpool_lrelu_bwd(const void* x, const float* gfeat, 
 extern "C" int spyr_gamma_residual_fwd(const void* t, const void* x, const float* gamma, void* out, void* out_act,
                                        float slope, long long n, void* stream) {
   SPYR_REQUIRE(n % 8 == 0, "gamma_residual_fwd: n must be a multiple of 8");
-  gamma_residual_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-      make_act(t, n), make_act(x, n), gamma, make_act(out, n), make_act(out_act, n), slope, n / 8);
+  SPYR_WITH_SPLIT(gamma_residual_fwd_kernel<kS><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      make_act(t, n), make_act(x, n), gamma, make_act(out, n), make_act(out_act, n), slope, n / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -964,8 +967,8 @@ extern "C" int spyr_gamma_residual_bwd(const void* g, const void* t, const float
   SPYR_REQUIRE(scratch != nullptr, "gamma_residual_bwd: scratch is NULL");
   int grid = grid_for(n / 8, 256);
   if (grid > SPYR_REDUCE_BLOCKS) grid = SPYR_REDUCE_BLOCKS;
-  gamma_residual_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(g, n), make_act(t, n), gamma, make_act(gt, n),
-                                                                    dgamma, n / 8, (float*)scratch, spyr_next_ticket());
+  SPYR_WITH_SPLIT(gamma_residual_bwd_kernel<kS><<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(g, n), make_act(t, n), gamma, make_act(gt, n),
+                                                                    dgamma, n / 8, (float*)scratch, spyr_next_ticket()));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -979,9 +982,13 @@ extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, fl
   const int prows = 256 / cg;
   const int threads = prows * cg;
   long long want = (rows + prows * 8 - 1) / (prows * 8);
-  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
-  colsum_kernel<<<grid, threads, (size_t)prows * C * 4, (cudaStream_t)stream>>>(make_act(g, rows * C), rows, cg, out0, out1,
-                                                                                out2, (float*)scratch, spyr_next_ticket());
+  // 4-byte partials: twice SPYR_REDUCE_BLOCKS vectors fit the 8-byte-slot scratch
+  int grid = (int)(want < 1 ? 1 : (want > 2 * SPYR_REDUCE_BLOCKS ? 2 * SPYR_REDUCE_BLOCKS : want));
+  SPYR_WITH_SPLIT(colsum_kernel<kS><<<grid, threads, (size_t)prows * C * 4, (cudaStream_t)stream>>>(make_act(g, rows * C), rows, cg,
+                                                                                (float*)scratch));
+  spyr_count_launch();
+  SumSink sk = {out0, out1, out2, 0, C, 0, 0, 0};
+  SPYR_CHECK_CUDA(spyr_launch_sum_partials((const float*)scratch, grid, C, sk, (cudaStream_t)stream));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -998,15 +1005,18 @@ extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H
   const size_t smem = (size_t)prows * 9 * C * 4;
   static bool configured = false;
   if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
   const long long npix = (long long)B * H * W;
   long long want = (npix + prows * 16 - 1) / (prows * 16);
-  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
-  stencil_wgrad_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mask, make_act(g, npix * C), B, H, W, cg, dw,
-                                                                      cin_stride, ci_row, (float*)scratch,
-                                                                      spyr_next_ticket());
+  int grid = (int)(want < 1 ? 1 : (want > 2 * SPYR_REDUCE_BLOCKS ? 2 * SPYR_REDUCE_BLOCKS : want));
+  SPYR_WITH_SPLIT(stencil_wgrad_kernel<kS><<<grid, threads, smem, (cudaStream_t)stream>>>(mask, make_act(g, npix * C), B, H, W, cg,
+                                                                      (float*)scratch));
+  spyr_count_launch();
+  SumSink sk = {dw, nullptr, nullptr, 1, C, cin_stride, ci_row, 0};
+  SPYR_CHECK_CUDA(spyr_launch_sum_partials((const float*)scratch, grid, 9 * C, sk, (cudaStream_t)stream));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1037,7 +1047,7 @@ extern "C" int spyr_wgrad_to_oihw(const float* gw, float* out, int taps, int Cin
 extern "C" int spyr_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset,
                                 float* y, void* y_bf16, unsigned char* mask, void* stream) {
   SPYR_REQUIRE(x && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments (0 <= p < 1)");
-  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, make_act(y_bf16, n), mask);
+  SPYR_WITH_SPLIT(dropout_fwd_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, offset, y, make_act(y_bf16, n), mask));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1050,7 +1060,7 @@ extern "C" int spyr_dropout_bwd(const float* g, const unsigned char* mask, long 
   return 0;
 }
 extern "C" int spyr_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
-  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, make_act(dst, n), n);
+  SPYR_WITH_SPLIT(cast_f32_bf16_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, make_act(dst, n), n));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1059,8 +1069,8 @@ extern "C" int spyr_vec_epilogue(const float* acc, int nsplit, const float* bias
                                  int mode, float* out_f32, void* out_bf16, int ld_bf16, int B, int N, void* stream) {
   SPYR_REQUIRE(acc && nsplit >= 1 && (mode != 2 || gate) && (out_bf16 == nullptr || ld_bf16 >= N),
                "vec_epilogue: bad arguments");
-  vec_epilogue_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, nsplit, bias, add, gate, mode, out_f32, make_act(out_bf16, (long long)B * ld_bf16), ld_bf16, B, N);
+  SPYR_WITH_SPLIT(vec_epilogue_kernel<kS><<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, nsplit, bias, add, gate, mode, out_f32, make_act(out_bf16, (long long)B * ld_bf16), ld_bf16, B, N));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1069,10 +1079,10 @@ extern "C" int spyr_conv2d_epilogue(const spyr_conv_desc* d, const float* acc, v
   SPYR_REQUIRE(d != nullptr && acc != nullptr, "conv2d_epilogue: bad arguments");
   SPYR_C8(d->Cout);
   const long long n = (long long)d->B * d->H * d->W * (d->Cout / 8);
-  conv_epilogue_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+  SPYR_WITH_SPLIT(conv_epilogue_kernel<kS><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       acc, d->splits < 1 ? 1 : d->splits, d->B, d->H, d->W, d->Cout / 8, d->bias, d->bias2, d->bias3, d->stencil_mask,
       d->stencil_w, make_act(d->dmask, n * 8), d->dmask_slope, make_act(d->residual, n * 8), make_act(d->y_raw, n * 8),
-      make_act(d->y_act, n * 8), d->act, d->act_slope);
+      make_act(d->y_act, n * 8), d->act, d->act_slope));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1084,11 +1094,11 @@ extern "C" int spyr_conv1x1_tanh_fwd(const void* a, const float* w, const float*
   const long long npix = (long long)B * HW;
   const size_t smem = (size_t)Cout * C * 4;
   if (Cout == 3)
-    conv1x1_tanh_fwd_kernel<3><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
-                                                                                         HW, C, npix);
+    SPYR_WITH_SPLIT(conv1x1_tanh_fwd_kernel<3, kS><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
+                                                                                         HW, C, npix));
   else
-    conv1x1_tanh_fwd_kernel<1><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
-                                                                                         HW, C, npix);
+    SPYR_WITH_SPLIT(conv1x1_tanh_fwd_kernel<1, kS><<<grid_for(npix, 128), 128, smem, (cudaStream_t)stream>>>(make_act(a, npix * C), w, sigma, bias, img,
+                                                                                         HW, C, npix));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -1107,17 +1117,18 @@ extern "C" int spyr_conv1x1_tanh_bwd(const float* gimg, const float* img, const 
   const size_t smem = ((size_t)Cout * C + (size_t)prows * Cout * C + (size_t)prows * Cout) * 4;
   SPYR_REQUIRE(smem <= 48 * 1024, "conv1x1_tanh_bwd: smem %zu too large", smem);
   long long want = (npix + prows * 16 - 1) / (prows * 16);
-  int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
-  unsigned int* ticket = spyr_next_ticket();
+  int grid = (int)(want < 1 ? 1 : (want > 2 * SPYR_REDUCE_BLOCKS ? 2 * SPYR_REDUCE_BLOCKS : want));
   if (Cout == 3)
-    conv1x1_tanh_bwd_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
-                                                                              make_act(gh, npix * C), dw, db, HW, C, npix,
-                                                                              (float*)scratch, ticket);
+    SPYR_WITH_SPLIT(conv1x1_tanh_bwd_kernel<3, kS><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
+                                                                              make_act(gh, npix * C), HW, C, npix,
+                                                                              (float*)scratch));
   else
-    conv1x1_tanh_bwd_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
-                                                                              make_act(gh, npix * C), dw, db, HW, C, npix,
-                                                                              (float*)scratch, ticket);
+    SPYR_WITH_SPLIT(conv1x1_tanh_bwd_kernel<1, kS><<<grid, threads, smem, (cudaStream_t)stream>>>(gimg, img, make_act(a, npix * C), w, sigma, slope,
+                                                                              make_act(gh, npix * C), HW, C, npix,
+                                                                              (float*)scratch));
   spyr_count_launch();
+  SumSink sk = {dw, db, nullptr, 2, C, 0, 0, Cout * C};
+  SPYR_CHECK_CUDA(spyr_launch_sum_partials((const float*)scratch, grid, Cout * C + Cout, sk, (cudaStream_t)stream));
   SPYR_LAUNCH_CHECK();
   return 0;
 }

@@ -27,7 +27,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---- attention softmax: one warp per query row ----
-__global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, const Act p, long long rows, int n) {
+template <bool S>
+__global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, const ActT<S> p, long long rows, int n) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -42,7 +43,8 @@ __global__ void softmax_rows_fwd_kernel(const float* __restrict__ s, const Act p
   for (int j = lane; j < n; j += 32) stf(p, (size_t)(row * n + j), __expf(sr[j] - m) * inv);
 }
 // dS = P * (dP - sum_k dP*P)
-__global__ void softmax_rows_bwd_kernel(const Act p, const float* __restrict__ dp, const Act ds,
+template <bool S>
+__global__ void softmax_rows_bwd_kernel(const ActT<S> p, const float* __restrict__ dp, const ActT<S> ds,
                                         long long rows, int n) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -74,13 +76,15 @@ __global__ void lsgan_bwd_kernel(const float* __restrict__ p, long long n, float
 }
 
 // ---- semantic reconstruction, one pyramid level: loss += mean(|maxpool2(fr) - maxpool2(ff)| * maxpool2(mask)) ----
-__device__ __forceinline__ void pool4(const Act& x, size_t off, size_t C, size_t WC, float v[4][8]) {
+template <bool S>
+__device__ __forceinline__ void pool4(const ActT<S>& x, size_t off, size_t C, size_t WC, float v[4][8]) {
   ld8(x + off, v[0]);
   ld8(x + off + C, v[1]);
   ld8(x + off + WC, v[2]);
   ld8(x + off + WC + C, v[3]);
 }
-__global__ void rec_level_fwd_kernel(const Act fr, const Act ff,
+template <bool S>
+__global__ void rec_level_fwd_kernel(const ActT<S> fr, const ActT<S> ff,
                                      const float* __restrict__ mask, int B, int H, int W, int cg, float inv_numel,
                                      float* __restrict__ loss, float* __restrict__ scratch, unsigned int* ticket) {
   __shared__ float red[32];
@@ -115,9 +119,10 @@ __global__ void rec_level_fwd_kernel(const Act fr, const Act ff,
     spyr_sum_partials<float>(scratch, (int)gridDim.x, 1, [&](int, float total) { *loss += total * inv_numel; });
 }
 // g_ff = d loss / d ff : -sign((pr - pf) * pm) * pm / numel * gout, routed to the first maximum of the 2x2 window
-__global__ void rec_level_bwd_kernel(const Act fr, const Act ff,
+template <bool S>
+__global__ void rec_level_bwd_kernel(const ActT<S> fr, const ActT<S> ff,
                                      const float* __restrict__ mask, int B, int H, int W, int cg, float inv_numel,
-                                     const float* __restrict__ gout, const Act gff) {
+                                     const float* __restrict__ gout, const ActT<S> gff) {
   const int OH = H / 2, OW = W / 2;
   const size_t C = (size_t)cg * 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,13 +289,13 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 }  // namespace
 
 extern "C" int spyr_softmax_rows_fwd(const float* s, void* p, long long rows, int n, void* stream) {
-  softmax_rows_fwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, make_act(p, rows * n), rows, n);
+  SPYR_WITH_SPLIT(softmax_rows_fwd_kernel<kS><<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(s, make_act(p, rows * n), rows, n));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int spyr_softmax_rows_bwd(const void* p, const float* dp, void* ds, long long rows, int n, void* stream) {
-  softmax_rows_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(make_act(p, rows * n), dp, make_act(ds, rows * n), rows, n);
+  SPYR_WITH_SPLIT(softmax_rows_bwd_kernel<kS><<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(make_act(p, rows * n), dp, make_act(ds, rows * n), rows, n));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -316,8 +321,8 @@ extern "C" int spyr_rec_level_fwd(const void* fr, const void* ff, const float* m
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
   long long want = (n + 1023) / 1024;
   const int grid = (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
-  rec_level_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B, H, W,
-                                                              C / 8, inv, loss, (float*)scratch, spyr_next_ticket());
+  SPYR_WITH_SPLIT(rec_level_fwd_kernel<kS><<<grid, 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B, H, W,
+                                                              C / 8, inv, loss, (float*)scratch, spyr_next_ticket()));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -328,8 +333,8 @@ extern "C" int spyr_rec_level_bwd(const void* fr, const void* ff, const float* m
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   SPYR_N32(n);
   const float inv = 1.f / ((float)B * (float)C * (float)(H / 2) * (float)(W / 2));
-  rec_level_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B,
-                                                                                 H, W, C / 8, inv, gout, make_act(gff, n * 32));
+  SPYR_WITH_SPLIT(rec_level_bwd_kernel<kS><<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_act(fr, n * 32), make_act(ff, n * 32), mask, B,
+                                                                                 H, W, C / 8, inv, gout, make_act(gff, n * 32)));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

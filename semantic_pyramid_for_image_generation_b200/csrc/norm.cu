@@ -84,7 +84,8 @@ __device__ __forceinline__ void build_gather_tables(Gather* tab, int H, int W, f
   __syncthreads();
 }
 
-__device__ __forceinline__ void up2_load(const Act& x, int b, int oh, int ow, int H, int W, int cg, int c, float sh,
+template <bool S>
+__device__ __forceinline__ void up2_load(const ActT<S>& x, int b, int oh, int ow, int H, int W, int cg, int c, float sh,
                                          float sw, float* v) {
   const Lerp Lh = lerp_src(oh, H, sh), Lw = lerp_src(ow, W, sw);
   float a[8], bq[8], cq[8], d[8];
@@ -102,9 +103,9 @@ __device__ __forceinline__ void up2_load(const Act& x, int b, int oh, int ow, in
 // ---------------------------------------------------------------------------------------------
 // The kernels below are templated on their mode: one body per mode keeps the plain same-resolution cases at ~40
 // registers (full occupancy) instead of inheriting the register count of the interpolating variants.
-template <int up2>
-__global__ void bn_stats_kernel(const Act x, int B, int H, int W, int cg, const Act xu_out,
-                                double* __restrict__ sums, double* __restrict__ scratch, unsigned int* ticket) {
+template <int up2, bool S>
+__global__ void bn_stats_kernel(const ActT<S> x, int B, int H, int W, int cg, const ActT<S> xu_out,
+                                double* __restrict__ partials) {
   extern __shared__ float sh[];  // [prows][2][C]
   const int C = cg * 8;
   const int c = threadIdx.x % cg;
@@ -129,7 +130,7 @@ __global__ void bn_stats_kernel(const Act x, int B, int H, int W, int cg, const 
         if (!xu_out.null()) {
           // materialise up2(x) once; the statistics are those of the stored values the later passes read
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = stored_value(v[j], xu_out.lo);
+          for (int j = 0; j < 8; ++j) v[j] = stored_value(v[j], xu_out);
           st8(xu_out + (p * cg + c) * 8, v);
         }
       } else {
@@ -149,25 +150,41 @@ __global__ void bn_stats_kernel(const Act x, int B, int H, int W, int cg, const 
     }
   }
   __syncthreads();
-  if (sums == nullptr) return;  // plain materialisation of up2(x)
+  if (partials == nullptr) return;  // plain materialisation of up2(x)
+  // one partial vector per block; bn_finalize adds them in block order (no atomics: bit-reproducible)
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < prows; ++r) s += (double)sh[r * 2 * C + i];
-    scratch[(size_t)blockIdx.x * 2 * C + i] = s;
+    partials[(size_t)blockIdx.x * 2 * C + i] = s;
   }
-  if (spyr_last_block(ticket, gridDim.x))
-    spyr_sum_partials<double>(scratch, (int)gridDim.x, 2 * C, [&](int i, double total) { sums[i] = total; });
 }
 
-// mean/rstd from the sums (train) or from the running buffers (eval); running-stat update as nn.BatchNorm2d
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+__device__ __forceinline__ double warp_tree_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// mean/rstd from the block partials of bn_stats (train: one warp per channel adds the nb partial sums lane-strided, then
+// a fixed xor tree) or from the running buffers (eval); running-stat update as nn.BatchNorm2d
+__global__ void bn_finalize_kernel(const double* __restrict__ partials, int nb, double count, int C, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float* __restrict__ mean_rstd, int training) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C && training) {
+    for (int b = lane; b < nb; b += 32) {
+      s1 += __ldcg(partials + (size_t)b * 2 * C + c);
+      s2 += __ldcg(partials + (size_t)b * 2 * C + C + c);
+    }
+  }
+  s1 = warp_tree_d(s1);
+  s2 = warp_tree_d(s2);
+  if (lane != 0) return;
   if (c < C) {
     if (training) {
-      const double mean = sums[c] / count;
-      double var = sums[C + c] / count - mean * mean;
+      const double mean = s1 / count;
+      double var = s2 / count - mean * mean;
       if (var < 0.0) var = 0.0;
       mean_rstd[c] = (float)mean;
       mean_rstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -192,11 +209,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // Channel-group-stationary: a thread keeps the affine parameters of its 8 channels (of ONE sample: blockIdx.y) in
 // registers and walks over output pixels, so the per-element work is one 16-byte load (four for the bilinear modes)
 // and one or two 16-byte stores.
-template <int mode>
-__global__ void bn_act_kernel(const Act x, const float* __restrict__ mean_rstd,
+template <int mode, bool S>
+__global__ void bn_act_kernel(const ActT<S> x, const float* __restrict__ mean_rstd,
                               const float* __restrict__ scale_ptr, const float* __restrict__ shift_ptr, int row_stride,
-                              const int* __restrict__ cls, float slope, const Act out_a,
-                              const Act out_xu, int H, int W, int cg) {
+                              const int* __restrict__ cls, float slope, const ActT<S> out_a,
+                              const ActT<S> out_xu, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = mode ? 2 * H : H, OW = mode ? 2 * W : W;
   const int b = blockIdx.y;
@@ -269,12 +286,12 @@ __global__ void bn_act_kernel(const Act x, const float* __restrict__ mean_rstd,
 //   mode 2: g is d/d(pre-LeakyReLU) at 2H x 2W (gate applied upstream): gy = up2^T(g), written to gy_out
 //   mode 3: g is d/dy at 2H x 2W and the normalised tensor is up2(x) (final block): reduce at 2H x 2W
 // ---------------------------------------------------------------------------------------------
-template <int mode>
-__global__ void bn_bwd_reduce_kernel(const Act g, const Act x,
+template <int mode, bool S>
+__global__ void bn_bwd_reduce_kernel(const ActT<S> g, const ActT<S> x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                      const float* __restrict__ shift_ptr, int row_stride, const int* __restrict__ cls,
-                                     float slope, const Act gy_out, float* __restrict__ S, int H, int W, int cg,
-                                     float* __restrict__ scratch, unsigned int* ticket) {
+                                     float slope, const ActT<S> gy_out, float* __restrict__ partials,
+                                     float* __restrict__ Sout, unsigned int* tickets, int H, int W, int cg) {
   extern __shared__ float sh[];  // [prows][2][C]
   __shared__ Gather gtab[GATHER_MAX];
   const int C = cg * 8;
@@ -355,7 +372,7 @@ __global__ void bn_bwd_reduce_kernel(const Act g, const Act x,
         }
         // the reduction uses the stored value that pass 2 will read back
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gy[j] = stored_value(gy[j], gy_out.lo);
+        for (int j = 0; j < 8; ++j) gy[j] = stored_value(gy[j], gy_out);
         st8(gy_out + off, gy);
       }
 #pragma unroll
@@ -375,18 +392,18 @@ __global__ void bn_bwd_reduce_kernel(const Act g, const Act x,
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < prows; ++r) s += sh[r * 2 * C + i];
-    scratch[((size_t)b * gridDim.x + blockIdx.x) * 2 * C + i] = s;
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 2 * C + i] = s;
   }
-  if (spyr_last_block(ticket, gridDim.x * gridDim.y)) {
-    for (int bb = 0; bb < (int)gridDim.y; ++bb)
-      spyr_sum_partials<float>(scratch + (size_t)bb * gridDim.x * 2 * C, (int)gridDim.x, 2 * C,
-                               [&](int i, float total) { S[(size_t)bb * 2 * C + i] = total; });
-  }
+  // the last block of THIS sample adds the sample's gridDim.x partial vectors in block order (one ticket per sample, so
+  // the B tails run in parallel): Sout[b][0][c] = sum gy, Sout[b][1][c] = sum gy * xhat -- no atomics on the data
+  if (spyr_last_block(tickets + b, gridDim.x))
+    spyr_sum_partials<float>(partials + (size_t)b * gridDim.x * 2 * C, (int)gridDim.x, 2 * C,
+                             [&](int i, float total) { Sout[(size_t)b * 2 * C + i] = total; });
 }
 
 // pass 1b: channel means M[0][c] = (1/N) sum_b scale[b,c] S1[b,c], M[1][c] likewise with S2, and the affine
 // parameter gradients: d_scale[row(b)][c] += S2[b,c], d_shift[row(b)][c] += S1[b,c]
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C, float count,
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ Sx, int B, int C, float count,
                                        const float* __restrict__ scale_ptr, int row_stride, const int* __restrict__ cls,
                                        float* __restrict__ M, float* __restrict__ d_scale, float* __restrict__ d_shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,7 +412,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
   for (int b = 0; b < B; ++b) {
     const int row = cls != nullptr ? cls[b] : 0;
     const float sc = scale_ptr[(size_t)row * row_stride + c];
-    const float a1 = S[((size_t)b * 2 + 0) * C + c], a2 = S[((size_t)b * 2 + 1) * C + c];
+    const float a1 = Sx[((size_t)b * 2 + 0) * C + c], a2 = Sx[((size_t)b * 2 + 1) * C + c];
     m1 += sc * a1;
     m2 += sc * a2;
     if (d_scale != nullptr) {
@@ -410,11 +427,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ S, int B, int C
 
 // pass 2: gx = rstd * (scale * gy - M1 - xhat * M2) (+ residual).  x_up2: gy/gx live at 2H x 2W and xhat is taken
 // from up2(x) (final block, where the statistics are those of the upsampled tensor)
-template <int x_up2>
-__global__ void bn_bwd_apply_kernel(const Act gy, const Act x,
+template <int x_up2, bool S>
+__global__ void bn_bwd_apply_kernel(const ActT<S> gy, const ActT<S> x,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ scale_ptr,
                                     int row_stride, const int* __restrict__ cls, const float* __restrict__ M,
-                                    const Act residual, const Act gx, int H, int W, int cg) {
+                                    const ActT<S> residual, const ActT<S> gx, int H, int W, int cg) {
   const int C = cg * 8;
   const int OH = x_up2 ? 2 * H : H, OW = x_up2 ? 2 * W : W;
   const int b = blockIdx.y;
@@ -465,7 +482,8 @@ __global__ void bn_bwd_apply_kernel(const Act gy, const Act x,
 }
 
 // plain transposed bilinear x2 (align_corners=True): g_lo = up2^T(g_hi)  (skip path of the generator block)
-__global__ void up2_bwd_kernel(const Act g, const Act out, int B, int H, int W, int cg) {
+template <bool S>
+__global__ void up2_bwd_kernel(const ActT<S> g, const ActT<S> out, int B, int H, int W, int cg) {
   __shared__ Gather gtab[GATHER_MAX];
   build_gather_tables(gtab, H, W, (float)(H - 1) / (float)(2 * H - 1), (float)(W - 1) / (float)(2 * W - 1));
   const long long n = (long long)B * H * W * cg;
@@ -528,6 +546,21 @@ __global__ void argmax_rows_kernel(const T* __restrict__ onehot, int n, int* __r
 struct Threads {
   int prows, threads;
 };
+inline Threads pick_threads(int cg, int max_threads);
+// grid of bn_stats (= number of partial vectors bn_finalize adds): a function of the problem shape only
+inline int bn_stats_blocks(long long npix, int cg) {
+  const int prows = 256 / cg < 1 ? 1 : 256 / cg;
+  long long want = (npix + prows * 16 - 1) / (prows * 16);
+  return (int)(want < 1 ? 1 : (want > SPYR_REDUCE_BLOCKS ? SPYR_REDUCE_BLOCKS : want));
+}
+// x-grid of bn_bwd_reduce (partial vectors per sample): B * gx <= 4 * SPYR_REDUCE_BLOCKS
+inline int bn_bwd_blocks(int npix_per_image, int cg, int B) {
+  const int prows = 256 / cg < 1 ? 1 : 256 / cg;
+  int gx = (npix_per_image + prows * 8 - 1) / (prows * 8);
+  const int cap = (4 * SPYR_REDUCE_BLOCKS) / B;
+  if (gx > cap) gx = cap;
+  return gx < 1 ? 1 : gx;
+}
 inline Threads pick_threads(int cg, int max_threads) {
   Threads t;
   t.prows = max_threads / cg;
@@ -540,49 +573,46 @@ inline Threads pick_threads(int cg, int max_threads) {
 
 #define SPYR_C8(C) SPYR_REQUIRE((C) > 0 && (C) % 8 == 0, "%s: channel count %d must be a multiple of 8", __func__, (int)(C))
 
-static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* scratch,
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* partials,
                            void* stream_);
 
-extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* sums, void* scratch, void* stream) {
-  return bn_stats_launch(x, B, H, W, C, up2, nullptr, sums, scratch, stream);
+extern "C" int spyr_bn_stats(const void* x, int B, int H, int W, int C, int up2, double* partials, void* stream) {
+  return bn_stats_launch(x, B, H, W, C, up2, nullptr, partials, stream);
 }
-extern "C" int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* sums, void* scratch,
-                              void* stream) {
+extern "C" int spyr_up2_stats(const void* x, int B, int H, int W, int C, void* xu_out, double* partials, void* stream) {
   SPYR_REQUIRE(xu_out != nullptr, "up2_stats: xu_out is NULL");
-  return bn_stats_launch(x, B, H, W, C, 1, xu_out, sums, scratch, stream);
+  return bn_stats_launch(x, B, H, W, C, 1, xu_out, partials, stream);
 }
-static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* sums, void* scratch,
+static int bn_stats_launch(const void* x, int B, int H, int W, int C, int up2, void* xu_out, double* partials,
                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_C8(C);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "bn_stats: C=%d too large", C);
-  SPYR_REQUIRE(sums == nullptr || scratch != nullptr, "bn_stats: scratch is NULL");
   const Threads t = pick_threads(cg, 256);
   const long long npix = (long long)B * H * W * (up2 ? 4 : 1);
+  // without statistics (plain materialisation of up2(x)) nothing is reduced: the grid is not bounded by the partials
   long long want = (npix + t.prows * 16 - 1) / (t.prows * 16);
-  // without statistics (plain materialisation of up2(x)) nothing is reduced: the grid is not bounded by the scratch
-  const int cap = sums != nullptr ? SPYR_REDUCE_BLOCKS : 1184;
-  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  const int grid = partials != nullptr ? bn_stats_blocks(npix, cg) : (int)(want < 1 ? 1 : (want > 1184 ? 1184 : want));
   const Act xa = make_act(x, (long long)B * H * W * C), xu = make_act(xu_out, npix * C);
-  unsigned int* ticket = spyr_next_ticket();
   if (up2)
-    bn_stats_kernel<1><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, sums, (double*)scratch,
-                                                                                ticket);
+    SPYR_WITH_SPLIT(bn_stats_kernel<1, kS><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, partials));
   else
-    bn_stats_kernel<0><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, sums, (double*)scratch,
-                                                                                ticket);
+    SPYR_WITH_SPLIT(bn_stats_kernel<0, kS><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(xa, B, H, W, cg, xu, partials));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int spyr_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+extern "C" int spyr_bn_finalize(const double* partials, double count, int C, float eps, float momentum, float* running_mean,
                                 float* running_var, long long* num_batches_tracked, float* mean_rstd, int training,
                                 void* stream) {
   SPYR_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, C, eps, momentum, running_mean,
-                                                                         running_var, num_batches_tracked, mean_rstd,
-                                                                         training);
+  SPYR_REQUIRE(!training || partials != nullptr, "bn_finalize: training mode needs the partial sums of spyr_bn_stats");
+  SPYR_C8(C);
+  const int nb = training ? bn_stats_blocks((long long)(count + 0.5), C / 8) : 0;  // the grid spyr_bn_stats used
+  bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nb, count, C, eps, momentum, running_mean,
+                                                                       running_var, num_batches_tracked, mean_rstd,
+                                                                       training);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -603,9 +633,9 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
   if (gx < 1) gx = 1;
   const long long nin = (long long)B * H * W * C, nout = (long long)B * npix * C;
 #define SPYR_BN_ACT(M)                                                                                                  \
-  bn_act_kernel<M><<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>(make_act(x, nin), mean_rstd, scale_ptr, shift_ptr, \
+  SPYR_WITH_SPLIT(bn_act_kernel<M, kS><<<dim3(gx, B), t.threads, 0, (cudaStream_t)stream>>>(make_act(x, nin), mean_rstd, scale_ptr, shift_ptr, \
                                                                         row_stride, cls, slope, make_act(out_a, nout),   \
-                                                                        make_act(out_xu, nout), H, W, cg)
+                                                                        make_act(out_xu, nout), H, W, cg))
   if (mode == 0) SPYR_BN_ACT(0);
   else if (mode == 1) SPYR_BN_ACT(1);
   else SPYR_BN_ACT(2);
@@ -616,7 +646,7 @@ extern "C" int spyr_bn_act(const void* x, const float* mean_rstd, const float* s
 }
 extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, const float* scale_ptr,
                                   const float* shift_ptr, int row_stride, const int* cls, float slope, int mode,
-                                  void* gy_out, float* S, int B, int H, int W, int C, void* scratch, void* stream_) {
+                                  void* gy_out, float* S, int B, int H, int W, int C, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_C8(C);
   SPYR_REQUIRE(mode == 0 || mode == 3 || gy_out != nullptr, "bn_bwd_reduce: modes 1/2 need gy_out");
@@ -624,22 +654,20 @@ extern "C" int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mea
   SPYR_REQUIRE((mode != 1 && mode != 2) || H + W <= GATHER_MAX, "bn_bwd_reduce: H + W = %d exceeds the gather table", H + W);
   const int cg = C / 8;
   SPYR_REQUIRE(cg <= 256, "bn_bwd_reduce: C=%d too large", C);
-  SPYR_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch is NULL");
+  SPYR_REQUIRE(S != nullptr, "bn_bwd_reduce: the partial-sum buffer is NULL");
   const Threads t = pick_threads(cg, 256);
   const int npix = H * W * (mode == 3 ? 4 : 1);
-  int gx = (npix + t.prows * 8 - 1) / (t.prows * 8);
-  const int cap = SPYR_REDUCE_BLOCKS / B;  // gx * B partial vectors of 2C floats must fit the scratch
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  SPYR_REQUIRE(gx * B <= SPYR_REDUCE_BLOCKS, "bn_bwd_reduce: batch %d exceeds %d", B, SPYR_REDUCE_BLOCKS);
+  const int gx = bn_bwd_blocks(npix, cg, B);  // B * gx partial vectors of 2C floats: SPYR_BN_BWD_PARTIAL_BYTES(C)
+  SPYR_REQUIRE(gx * B <= 4 * SPYR_REDUCE_BLOCKS, "bn_bwd_reduce: batch %d exceeds %d", B, 4 * SPYR_REDUCE_BLOCKS);
   dim3 grid(gx, B);
+  unsigned int* tickets = spyr_next_tickets(B);  // one per sample
+  SPYR_REQUIRE(tickets != nullptr, "bn_bwd_reduce: batch %d exceeds the ticket pool", B);
   // H, W are x's dims; g lives at 2H x 2W in modes 1, 2 and 3, gy_out (modes 1, 2) at H x W
   const long long nx = (long long)B * H * W * C, ng = (mode == 1 || mode == 2) ? 4 * nx : (mode == 3 ? 4 * nx : nx);
-  unsigned int* ticket = spyr_next_ticket();
 #define SPYR_BN_RED(M)                                                                  \
-  bn_bwd_reduce_kernel<M><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(     \
-      make_act(g, ng), make_act(x, nx), mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, make_act(gy_out, nx), S, \
-      H, W, cg, (float*)scratch, ticket)
+  SPYR_WITH_SPLIT(bn_bwd_reduce_kernel<M, kS><<<grid, t.threads, (size_t)t.prows * 2 * C * 4, stream>>>(     \
+      make_act(g, ng), make_act(x, nx), mean_rstd, scale_ptr, shift_ptr, row_stride, cls, slope, make_act(gy_out, nx),  \
+      S + (size_t)B * 2 * C, S, tickets, H, W, cg))
   if (mode == 0) SPYR_BN_RED(0);
   else if (mode == 1) SPYR_BN_RED(1);
   else if (mode == 2) SPYR_BN_RED(2);
@@ -671,13 +699,13 @@ extern "C" int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mea
   if (gxx < 1) gxx = 1;
   const long long nx = (long long)B * H * W * C, ng = (long long)B * npix * C;
   if (x_up2)
-    bn_bwd_apply_kernel<1><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
+    SPYR_WITH_SPLIT(bn_bwd_apply_kernel<1, kS><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
         make_act(gy, ng), make_act(x, nx), mean_rstd, scale_ptr, row_stride, cls, M, make_act(residual, ng), make_act(gx, ng),
-        H, W, cg);
+        H, W, cg));
   else
-    bn_bwd_apply_kernel<0><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
+    SPYR_WITH_SPLIT(bn_bwd_apply_kernel<0, kS><<<dim3(gxx, B), t.threads, 0, (cudaStream_t)stream>>>(
         make_act(gy, ng), make_act(x, nx), mean_rstd, scale_ptr, row_stride, cls, M, make_act(residual, ng), make_act(gx, ng),
-        H, W, cg);
+        H, W, cg));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
@@ -690,7 +718,7 @@ extern "C" int spyr_up2_bwd(const void* g_hi, void* g_lo, int B, int H, int W, i
   SPYR_REQUIRE(H + W <= GATHER_MAX, "up2_bwd: H + W = %d exceeds the gather table (%d)", H + W, GATHER_MAX);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;  // the tables are built once per block: a few blocks per SM, grid-stride loop
-  up2_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_act(g_hi, n * 32), make_act(g_lo, n * 8), B, H, W, C / 8);
+  SPYR_WITH_SPLIT(up2_bwd_kernel<kS><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(make_act(g_hi, n * 32), make_act(g_lo, n * 8), B, H, W, C / 8));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;

@@ -33,7 +33,9 @@ __device__ __forceinline__ int find_layer(const spyr_sn_layer* tab, int n, int t
   if (threadIdx.x == 0) {
     int l = 0;
     for (int i = 0; i < n; ++i) {
-      const int t0 = which == 0 ? tab[i].tile0_wtu : (which == 1 ? tab[i].tile0_wv : (which == 2 ? tab[i].tile0_pack : tab[i].tile0_bwd));
+      const int t0 = which == 0 ? tab[i].tile0_wtu
+                     : (which == 1 ? tab[i].tile0_wv
+                                   : (which == 2 ? tab[i].tile0_pack : (which == 3 ? tab[i].tile0_bwd : tab[i].tile0_tsum)));
       if (t0 <= tile) l = i;
     }
     *sh_idx = l;
@@ -42,27 +44,41 @@ __device__ __forceinline__ int find_layer(const spyr_sn_layer* tab, int n, int t
   return *sh_idx;
 }
 
-constexpr int WTU_COLS = 64, WTU_GROUPS = 4;  // 256 threads: 64 columns x 4 interleaved row groups
+constexpr int WTU_ROWS = 64, WTU_COLS = 256;
 
-// t[j] = sum_i W[i][j] u[i].  One CTA owns 64 columns and ALL rows of its layer: no sum crosses a CTA, so the result
-// does not depend on scheduling (the row groups of a CTA are combined in a fixed order).
+// partial[rt][j] = sum_{i in row tile rt} W[i][j] u[i]: one CTA per (row tile, 256 columns), plain stores into the layer's
+// partial slices; sn_tsum_kernel adds the row tiles in order (no atomics: bit-reproducible)
 __global__ void sn_wtu_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch) {
   __shared__ int sh_idx;
-  __shared__ float part[WTU_GROUPS][WTU_COLS];
+  __shared__ float su[WTU_ROWS];
   const int l = find_layer(tab, n, blockIdx.x, 0, &sh_idx);
   const spyr_sn_layer L = tab[l];
-  const int c0 = (blockIdx.x - L.tile0_wtu) * WTU_COLS;
-  const int cj = threadIdx.x % WTU_COLS, rg = threadIdx.x / WTU_COLS;
-  const int j = c0 + cj;
-  float acc = 0.f;
-  if (j < L.cols) {
-    const float* wp = L.w + j;
-#pragma unroll 8
-    for (int i = rg; i < L.rows; i += WTU_GROUPS) acc += __ldg(wp + (size_t)i * L.cols) * __ldg(L.u + i);
-  }
-  part[rg][cj] = acc;
+  const int tile = blockIdx.x - L.tile0_wtu;
+  const int ctiles = (L.cols + WTU_COLS - 1) / WTU_COLS;
+  const int rt = tile / ctiles;
+  const int r0 = rt * WTU_ROWS, c0 = (tile % ctiles) * WTU_COLS;
+  const int nr = min(WTU_ROWS, L.rows - r0);
+  if (threadIdx.x < nr) su[threadIdx.x] = L.u[r0 + threadIdx.x];
   __syncthreads();
-  if (rg == 0 && j < L.cols) scratch[L.scratch_off + j] = (part[0][cj] + part[1][cj]) + (part[2][cj] + part[3][cj]);
+  const int j = c0 + threadIdx.x;
+  if (j >= L.cols) return;
+  const float* wp = L.w + (size_t)r0 * L.cols + j;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < nr; ++i) acc += wp[(size_t)i * L.cols] * su[i];
+  scratch[L.part_off + (size_t)rt * L.cols + j] = acc;
+}
+// t[j] = sum over the row tiles (in order) of partial[rt][j]
+__global__ void sn_tsum_kernel(const spyr_sn_layer* __restrict__ tab, int n, float* __restrict__ scratch) {
+  __shared__ int sh_idx;
+  const int l = find_layer(tab, n, blockIdx.x, 4, &sh_idx);
+  const spyr_sn_layer L = tab[l];
+  const int j = (blockIdx.x - L.tile0_tsum) * blockDim.x + threadIdx.x;
+  if (j >= L.cols) return;
+  const int rtiles = (L.rows + WTU_ROWS - 1) / WTU_ROWS;
+  float acc = 0.f;
+  for (int rt = 0; rt < rtiles; ++rt) acc += scratch[L.part_off + (size_t)rt * L.cols + j];
+  scratch[L.scratch_off + j] = acc;
 }
 
 constexpr int WV_ROWS = 8;  // one weight row per warp
@@ -297,7 +313,7 @@ __global__ void sn_bwd_kernel(const spyr_sn_layer* __restrict__ tab, int n, cons
 
 extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
   SPYR_REQUIRE(tab != nullptr && out != nullptr && n > 0, "sn_plan: bad arguments");
-  int t_wtu = 0, t_wv = 0, t_pack = 0, t_bwd = 0;
+  int t_wtu = 0, t_wv = 0, t_pack = 0, t_bwd = 0, t_tsum = 0;
   long long scratch = 0, saved = 0;
   for (int i = 0; i < n; ++i) {
     spyr_sn_layer& L = tab[i];
@@ -305,7 +321,9 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     SPYR_REQUIRE(L.taps <= 9, "sn_plan: layer %d has %d taps", i, L.taps);
     L.index = i;
     L.tile0_wtu = t_wtu;
-    t_wtu += ceil_div(L.cols, WTU_COLS);
+    t_wtu += ceil_div(L.rows, WTU_ROWS) * ceil_div(L.cols, WTU_COLS);
+    L.tile0_tsum = t_tsum;
+    t_tsum += ceil_div(L.cols, 256);
     L.tile0_wv = t_wv;
     t_wv += ceil_div(L.rows, WV_ROWS);
     L.tile0_pack = t_pack;
@@ -314,11 +332,13 @@ extern "C" int spyr_sn_plan(spyr_sn_layer* tab, int n, spyr_sn_plan_out* out) {
     t_bwd += ceil_div(L.rows, BT) * ceil_div(L.cin, sn_btc(L.taps));
     L.scratch_off = scratch;  // 16-byte aligned so the power-iteration vector can be read as float4
     scratch += (L.cols + L.rows + 3) & ~3;
+    L.part_off = scratch;  // row-tile partial sums of W^T u
+    scratch += ((long long)ceil_div(L.rows, WTU_ROWS) * L.cols + 3) & ~3;
     L.saved_off = saved;
     saved += 1 + L.rows + L.cols;
   }
-  SPYR_REQUIRE(WTU_COLS * WTU_GROUPS == 256, "sn_plan: power-iteration tile shape");
   out->tiles_wtu = t_wtu;
+  out->tiles_tsum = t_tsum;
   out->tiles_wv = t_wv;
   out->tiles_pack = t_pack;
   out->tiles_bwd = t_bwd;
@@ -332,7 +352,10 @@ extern "C" int spyr_sn_forward(const spyr_sn_layer* dev_tab, int n, const spyr_s
   cudaStream_t stream = (cudaStream_t)stream_;
   SPYR_REQUIRE(dev_tab && plan && scratch && saved && n > 0, "sn_forward: bad arguments");
   if (training) {
-    sn_wtu_kernel<<<plan->tiles_wtu, WTU_COLS * WTU_GROUPS, 0, stream>>>(dev_tab, n, scratch);
+    sn_wtu_kernel<<<plan->tiles_wtu, WTU_COLS, 0, stream>>>(dev_tab, n, scratch);
+    spyr_count_launch();
+    SPYR_LAUNCH_CHECK();
+    sn_tsum_kernel<<<plan->tiles_tsum, 256, 0, stream>>>(dev_tab, n, scratch);
     spyr_count_launch();
     SPYR_LAUNCH_CHECK();
   }

@@ -177,11 +177,10 @@ def _cbn_backward(cbn, ga, grad, x, mr, cls, g, mode, residual=None):
     B, H, W, Cc = x.shape
     emb = cbn.embedding.weight
     sp, hp = emb.data_ptr(), emb.data_ptr() + 4 * Cc
-    S = torch.empty((B, 2, Cc), dtype=F32, device=x.device)
+    S = ops.bn_bwd_partials(B, H * W, Cc, x.device)
     gy = ops.act_like(x) if mode else g
-    sc = ops.scratch(2 * Cc, x.device)
     call("spyr_bn_bwd_reduce", g.data_ptr(), x.data_ptr(), mr.data_ptr(), sp, hp, 2 * Cc, cls.data_ptr(), LRELU, mode,
-         gy.data_ptr() if mode else None, S.data_ptr(), B, H, W, Cc, sc.data_ptr())
+         gy.data_ptr() if mode else None, S.data_ptr(), B, H, W, Cc)
     M = torch.empty(2 * Cc, dtype=F32, device=x.device)
     ge = ga.ptr(grad, emb)
     call("spyr_bn_bwd_finalize", S.data_ptr(), B, Cc, float(B * H * W), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(), ge,
@@ -346,14 +345,13 @@ def generator_backward(G, ctx, g_img):
     ops.colsum(g_h3, c5, ga.ptr(grad, f3.bias))
     g_pre, _ = ops.conv(B, 2 * H, 2 * W, c5, [Src(g_h3, st.w("final_block.3"), c5, 3, mn=True)], dmask=a,
                         dmask_slope=LRELU)
-    S = torch.empty((B, 2, c5), dtype=F32, device=dev)
     wp, bp = bn.weight.data_ptr(), bn.bias.data_ptr()
     xu = ctx.get("xu")
     # training forward: BN ran on the materialised up2(x) -> plain reductions at 2H x 2W; eval forward: x interpolated
     xs, hs, ws, mode = (xu, 2 * H, 2 * W, 0) if xu is not None else (x, H, W, 3)
-    sc2 = ops.scratch(2 * c5, dev)
+    S = ops.bn_bwd_partials(B, 4 * H * W, c5, dev)
     call("spyr_bn_bwd_reduce", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, bp, 0, None, LRELU, mode, None,
-         S.data_ptr(), B, hs, ws, c5, sc2.data_ptr())
+         S.data_ptr(), B, hs, ws, c5)
     M = torch.empty(2 * c5, dtype=F32, device=dev)
     call("spyr_bn_bwd_finalize", S.data_ptr(), B, c5, float(B * 4 * H * W), wp, 0, None, M.data_ptr(),
          ga.ptr(grad, bn.weight), ga.ptr(grad, bn.bias))

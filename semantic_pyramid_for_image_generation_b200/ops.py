@@ -109,7 +109,8 @@ def _profiled(kernel, flops, nbytes, name, desc, label=""):
     e0.record()
     call(name, desc)
     e1.record()
-    PROFILE.append((kernel, flops, nbytes, e0, e1, label))
+    real = N.lib().spyr_last_conv_kernel().decode() or kernel  # the kernel the dispatcher actually chose
+    PROFILE.append((real, flops, nbytes, e0, e1, label))
 
 
 class LeafStream(object):
@@ -381,9 +382,8 @@ def maxpool2_bwd(x, gy, relu_gate, out=None):
 
 def bn_stats(x, up2=False):
     B, H, W, Cc = x.shape
-    sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
-    sc = scratch(2 * Cc, x.device)
-    call("spyr_bn_stats", x.data_ptr(), B, H, W, Cc, int(up2), sums.data_ptr(), sc.data_ptr())
+    sums = scratch(2 * Cc, x.device)  # per-block partial sums (FP64); bn_finalize adds them in block order
+    call("spyr_bn_stats", x.data_ptr(), B, H, W, Cc, int(up2), sums.data_ptr())
     return sums
 
 
@@ -391,10 +391,28 @@ def up2_stats(x):
     """xu = up2(x) (bilinear, align_corners=True) materialised in BF16 together with its per-channel sum / sum of squares."""
     B, H, W, Cc = x.shape
     xu = act_empty((B, 2 * H, 2 * W, Cc), x.device)
-    sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
-    sc = scratch(2 * Cc, x.device)
-    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), sums.data_ptr(), sc.data_ptr())
+    sums = scratch(2 * Cc, x.device)
+    call("spyr_up2_stats", x.data_ptr(), B, H, W, Cc, xu.data_ptr(), sums.data_ptr())
     return xu, sums
+
+
+def bn_stats_blocks(npix, Cc):
+    """Number of partial vectors spyr_bn_stats writes for `npix` pixels (mirrors bn_stats_blocks in csrc/norm.cu)."""
+    prows = max(1, 256 // (Cc // 8))
+    return max(1, min((npix + prows * 16 - 1) // (prows * 16), N.REDUCE_BLOCKS))
+
+
+def bn_sums(partials, npix, Cc):
+    """(sum, sum of squares) per channel from the partials of bn_stats / up2_stats, as FP64 [2C] (tests, debugging)."""
+    nb = bn_stats_blocks(npix, Cc)
+    return partials.view(torch.float64)[:nb * 2 * Cc].view(nb, 2 * Cc).sum(dim=0)
+
+
+def bn_bwd_partials(B, npix_per_image, Cc, device):
+    """Buffer for the block partials of spyr_bn_bwd_reduce ([B][gx][2][C] FP32; gx mirrors bn_bwd_blocks in csrc/norm.cu)."""
+    prows = max(1, 256 // (Cc // 8))
+    gx = max(1, min((npix_per_image + prows * 8 - 1) // (prows * 8), (4 * N.REDUCE_BLOCKS) // B))
+    return torch.empty(B * (gx + 1) * 2 * Cc, dtype=F32, device=device)  # [B][2][C] sums + [B][gx][2][C] partials
 
 
 def bn_finalize(sums, count, Cc, eps, momentum, running_mean, running_var, nbt, training):
@@ -409,8 +427,19 @@ def bn_act(x, mean_rstd, scale_ptr, shift_ptr, row_stride, cls, mode, want_xu=Fa
     f = 2 if mode else 1
     a = act_empty((B, H * f, W * f, Cc), x.device)
     xu = act_empty((B, H * f, W * f, Cc), x.device) if want_xu else None
-    call("spyr_bn_act", x.data_ptr(), mean_rstd.data_ptr(), scale_ptr, shift_ptr, row_stride, ptr(cls), slope, mode,
-         a.data_ptr(), ptr(xu), B, H, W, Cc)
+    if PROFILE is None:
+        call("spyr_bn_act", x.data_ptr(), mean_rstd.data_ptr(), scale_ptr, shift_ptr, row_stride, ptr(cls), slope, mode,
+             a.data_ptr(), ptr(xu), B, H, W, Cc)
+    else:
+        # bandwidth-bound pass: algorithmic bytes = x read once + every output written once (per plane)
+        planes = 2 if SPLIT else 1
+        nbytes = 2 * planes * (x.numel() + a.numel() + (xu.numel() if xu is not None else 0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("spyr_bn_act", x.data_ptr(), mean_rstd.data_ptr(), scale_ptr, shift_ptr, row_stride, ptr(cls), slope, mode,
+             a.data_ptr(), ptr(xu), B, H, W, Cc)
+        e1.record()
+        PROFILE.append(("bn_act_kernel<%d>" % mode, 0.0, float(nbytes), e0, e1, "B%d %dx%d C=%d" % (B, H, W, Cc)))
     return a, xu
 
 

@@ -174,8 +174,9 @@ def test_gradient_arena_and_spectral_norm_plan():
         tab[i].pack_cin = cin if taps == 9 else 0
     plan = N.SnPlan()
     N.call_nostream("spyr_sn_plan", tab, 2, C.byref(plan))
-    # power iteration: one CTA per 64 columns owning all rows (no cross-CTA sums: deterministic)
-    assert plan.tiles_wtu == 9 + 2 and plan.tiles_wv == 8 + 46 and plan.tiles_pack == 64 + 1
+    # power iteration: (row tile, 256 columns) CTAs store partial sums, sn_tsum adds the row tiles in order
+    assert plan.tiles_wtu == 1 * 3 + 6 * 1 and plan.tiles_tsum == 3 + 1 and plan.tiles_wv == 8 + 46
+    assert plan.tiles_pack == 64 + 1
     assert plan.saved_floats == (1 + 64 + 576) + (1 + 365 + 128)
     # offsets follow the module's CURRENT parameter objects: a deep copy (an EMA generator, say) keeps working
     import copy
@@ -290,11 +291,11 @@ def test_gradient_reducer_world_size_2_gloo(tmp_path):
 def test_bench_reference_arm_prints_contract_line():
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
-                          "1"], capture_output=True, text=True, check=True, cwd=ROOT)
+                          "1", "--cpu-batch", "2"], capture_output=True, text=True, check=True, cwd=ROOT)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] and line["steps_timed"] == 1
 
 
 def test_packed_mask_descriptors_round_trip():
