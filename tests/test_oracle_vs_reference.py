@@ -238,3 +238,77 @@ def test_checkpoint_interchange_with_reference_modules(ref, tmp_path):
     v_ref, v_new = ref_models.VGG16(), new_models.VGG16()
     v_new.load_state_dict(v_ref.state_dict())
     v_ref.load_state_dict(v_new.state_dict())
+
+
+def _realistic_running_stats(g_sd, z, feats, masks, cls, seed=17):
+    """Fills the batch-norm running statistics with what a long training run would hold: the batch statistics of a
+    training-mode forward (momentum forced to 1), jittered by 10 %% so that eval mode is distinguishable from train mode.
+    (With the constructor's mean 0 / var 1 a random-init generator saturates tanh everywhere and eval parity is vacuous.)"""
+    from unittest import mock
+    real = O._bn_train
+    with mock.patch.object(O, "_bn_train", lambda x, sd, prefix, momentum, training: real(x, sd, prefix, 1.0, training)):
+        with torch.no_grad():
+            O.generator_forward(g_sd, z, feats, masks, cls, training=True)
+    gen = torch.Generator().manual_seed(seed)
+    for k, v in g_sd.items():
+        if k.endswith("running_mean"):
+            v.add_(0.1 * v.abs().mean() * torch.randn(v.shape, generator=gen))
+        elif k.endswith("running_var"):
+            v.mul_(1.0 + 0.1 * (2 * torch.rand(v.shape, generator=gen) - 1))
+
+
+def test_eval_mode_generator_matches_reference(ref):
+    """Pins the oracle's eval-mode generator (running batch-norm statistics, no power iteration: what `inference()` and
+    `validate()` run, model_wrapper.py:231-296) against the reference's `generator.eval()`."""
+    models, _, _ = ref
+    cf = 2
+    g_sd = O.init_generator_state(cf, seed=3)
+    images, labels, masks, z, _ = O.synthetic_batch(2, seed=2, mask_mode="inference")
+    feats = O.vgg16_features(O.init_vgg_state(seed=5), images)
+    _realistic_running_stats(g_sd, z, feats, masks, labels.float())
+    g = models.Generator(channels_factor=cf)
+    g.load_state_dict(_clone(g_sd))
+    g.eval()
+    before = _clone(g_sd)
+    with torch.no_grad():
+        theirs = g(input=z, features=feats, masks=masks, class_id=labels.float())
+        mine = O.generator_forward(g_sd, z, feats, masks, labels.float(), training=False)
+    assert torch.allclose(theirs, mine, rtol=1e-4, atol=1e-5)
+    assert float(mine.abs().mean()) < 0.9  # not saturated: the comparison means something
+    for k in g_sd:  # eval mode leaves u, v and the running statistics untouched
+        assert torch.equal(g_sd[k], before[k]), k
+
+
+def test_data_parallel_oracle_reduces_to_the_single_process_step():
+    """train_step_data_parallel (reference step per shard, gradients averaged) with ONE replica is train_step,
+    and with two replicas each phase's gradient is the mean of the per-shard gradients of the phase functions."""
+    cf = 2
+    images, labels, masks, z_d, z_g = O.synthetic_batch(2, seed=4, mask_mode="inference")
+    v_sd = O.init_vgg_state(seed=5)
+    g1, d1 = O.init_generator_state(cf, seed=3), O.init_discriminator_state(cf, seed=4)
+    g2, d2 = _clone(g1), _clone(d1)
+    a = O.train_step(g1, d1, v_sd, images, labels, masks, z_d, z_g, {}, {}, lr=1e-4)
+    b = O.train_step_data_parallel([(g2, d2)], v_sd, [(images, labels, masks, z_d, z_g)], {}, {}, lr=1e-4)[0]
+    for k in ("loss_discriminator_real", "loss_generator", "loss_generator_semantic_reconstruction",
+              "loss_generator_diversity"):
+        assert a[k] == b[k], k
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+    for k in d1:
+        assert torch.equal(d1[k], d2[k]), k
+    # two replicas, one sample each: the D-phase gradient is the mean of the two per-shard gradients
+    shards = []
+    for r in range(2):
+        im, lb, mk, zd, zg = O.synthetic_batch(2, seed=10 + r, mask_mode="inference")
+        shards.append((im, lb, mk, zd, zg))
+    g0, d0 = O.init_generator_state(cf, seed=3), O.init_discriminator_state(cf, seed=4)
+    per_shard = []
+    for sh in shards:
+        _, _, _, gr = O._discriminator_phase(_clone(g0), _clone(d0), v_sd, sh[0], sh[1], sh[2], sh[3])
+        per_shard.append(gr)
+    reps = [(_clone(g0), _clone(d0)), (_clone(g0), _clone(d0))]
+    out = O.train_step_data_parallel(reps, v_sd, shards, {}, {}, lr=1e-4)
+    for k in per_shard[0]:
+        assert torch.allclose(out[0]["d_grads"][k], (per_shard[0][k] + per_shard[1][k]) / 2, rtol=0, atol=0), k
+    for k in O.trainable_keys(reps[0][1]):
+        assert torch.equal(reps[0][1][k], reps[1][1][k]), k  # replicas stay identical after the update
