@@ -321,3 +321,25 @@ def test_packed_mask_descriptors_round_trip():
             assert torch.equal(got, want)
     with pytest.raises(ValueError):
         ip.PackedDescriptors(2, pin=False).fill(descs[:3])
+
+
+def test_main_py_keeps_the_reference_flags_and_replaces_dataparallel_by_torchrun():
+    """main.py mirrors reference main.py:4-42 (twelve flags, same defaults) and `--use_data_parallel` becomes a one-process-
+    per-GPU torchrun launch instead of nn.DataParallel (main.py:91-94)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spyr_main", os.path.join(ROOT, "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    args = mod.build_parser().parse_args([])
+    reference_defaults = dict(train=False, test=False, batch_size=20, lr=1e-05, channel_factor=1.0, device='cuda',
+                              gpus_to_use='0', use_data_parallel=False, load_checkpoint=None,
+                              load_pretrained_vgg16='pre_trained_models/vgg_places_365_fine_tuned.pt',
+                              path_to_places365='places365_standard', epochs=50)
+    for k, v in reference_defaults.items():
+        assert getattr(args, k) == v, k
+    env = dict(os.environ, SPYR_MAIN_DRY_RUN="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--train", "--use_data_parallel", "--gpus_to_use",
+                          "0,1,2,3", "--batch_size", "20"], capture_output=True, text=True, check=True, env=env, cwd=ROOT)
+    cmd = out.stdout.strip()
+    assert "torch.distributed.run" in cmd and "--nproc-per-node 4" in cmd and "--master-addr 127.0.0.1" in cmd
+    assert cmd.endswith("--train --use_data_parallel --gpus_to_use 0,1,2,3 --batch_size 20")

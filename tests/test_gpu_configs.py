@@ -227,3 +227,16 @@ def test_two_rank_step_matches_sharded_oracle(tmp_path):
         e = (num / den) ** 0.5
         print("%s: Adam update of the averaged gradient, rel-L2 vs oracle %.3e" % (which, e))
         assert e < 0.3, e  # sign-like first Adam step: see test_full_step_at_benchmark_batch_matches_oracle
+
+
+def test_main_py_trains_on_synthetic_data(tmp_path):
+    """The drop-in CLI end to end: `python main.py --train --synthetic 4 ...` (reference main.py:58-107 over this package)."""
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--train", "--synthetic", "4", "--batch_size", "2",
+                          "--epochs", "1", "--channel_factor", "2"], capture_output=True, text=True, cwd=str(tmp_path),
+                         timeout=600)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    assert "Number of generator parameters" in run.stdout
+    saved = os.listdir(str(tmp_path / "saved_data"))
+    assert any(name.startswith("models_") for name in saved)
+    ckpt_dir = [n for n in saved if n.startswith("models_")][0]
+    assert os.listdir(str(tmp_path / "saved_data" / ckpt_dir)) == ["checkpoint_000.pt"]
