@@ -142,6 +142,28 @@ typedef struct {
 long long spyr_conv2d_wgrad_scratch_floats(const spyr_wgrad_desc* d); /* host only; -1 on a bad descriptor */
 int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream);
 
+/* Deferred second stages.  A backward pass launches ~90 weight gradients and ~55 bias / mask-channel sums, each followed
+ * by a small kernel that adds its partial results in a fixed order.  The *_deferred entry points launch only the first
+ * stage and describe the pending sum in `out`; spyr_reduce_batched then performs up to SPYR_REDUCE_BATCH pending sums in
+ * ONE launch (same arithmetic, same order: bit-identical to the immediate form).  out->kind == 0 means nothing is pending
+ * (a single slice was accumulated directly). */
+typedef struct {
+  int kind;                 /* 0 none, 1 weight-gradient slices (float4 lanes), 2 partial vectors (one warp per output) */
+  const float* partial;     /* kind 1: [nslices][nimg][taps*cin_stride*Cout];  kind 2: [nb][n] */
+  float* out0;              /* kind 1: dw;  kind 2: first destination */
+  float* out1;
+  float* out2;
+  int nslices, nimg, taps, rows, cin_stride, Cout, lanes; /* kind 1 */
+  int nb, n, mode, C, sink_stride, sink_row, split;       /* kind 2: SumSink of csrc/common.cuh */
+} spyr_reduce_entry;
+#define SPYR_REDUCE_BATCH 32
+int spyr_conv2d_wgrad_deferred(const spyr_wgrad_desc* d, spyr_reduce_entry* out, void* stream);
+int spyr_colsum_deferred(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* scratch,
+                         spyr_reduce_entry* out, void* stream);
+int spyr_stencil_wgrad_deferred(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride,
+                                int ci_row, void* scratch, spyr_reduce_entry* out, void* stream);
+int spyr_reduce_batched(const spyr_reduce_entry* entries, int n, void* stream); /* n <= SPYR_REDUCE_BATCH */
+
 /* ------------------------------------------------------------------------------------------------
  * Image <-> first-layer operand.  The 3-channel 3x3 convolutions (VGG features.0, models.py:201; Discriminator
  * layers.0.main_block.0, models.py:393) run as a 1x1 tensor-core conv over 32-wide im2col rows

@@ -134,7 +134,7 @@ def main(argv=None):
         rank = reducer.rank if reducer is not None else 0
         lo, hi = distributed.shard_range(args.synthetic, rank, world)
         train_set = torch.utils.data.Subset(SyntheticPlaces(args.synthetic), range(lo, hi))
-        val_set = torch.utils.data.Subset(SyntheticPlaces(args.synthetic), range(0, min(args.synthetic, 14)))
+        val_set = SyntheticPlaces(14)  # inference() draws 7 distinct validation samples (model_wrapper.py:258)
         collate_fn = collate
     else:
         import data  # the user's loader module (reference data.py); outside this package's scope

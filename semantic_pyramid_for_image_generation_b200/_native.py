@@ -34,6 +34,16 @@ class WgradDesc(C.Structure):
                 ("scratch_floats", c_ll)]
 
 
+class ReduceEntry(C.Structure):
+    _fields_ = [("kind", c_int), ("partial", c_void_p), ("out0", c_void_p), ("out1", c_void_p), ("out2", c_void_p),
+                ("nslices", c_int), ("nimg", c_int), ("taps", c_int), ("rows", c_int), ("cin_stride", c_int),
+                ("Cout", c_int), ("lanes", c_int), ("nb", c_int), ("n", c_int), ("mode", c_int), ("C", c_int),
+                ("sink_stride", c_int), ("sink_row", c_int), ("split", c_int)]
+
+
+REDUCE_BATCH = 32  # SPYR_REDUCE_BATCH
+
+
 class SnLayer(C.Structure):
     _fields_ = [("w", c_void_p), ("u", c_void_p), ("v", c_void_p), ("rows", c_int), ("cols", c_int), ("taps", c_int),
                 ("cin", c_int), ("pack_cin", c_int), ("pack_mode", c_int), ("pack_off", c_ll), ("stencil_off", c_ll),
@@ -61,6 +71,10 @@ _SIGNATURES = {
     "spyr_conv2d_fprop": [C.POINTER(ConvDesc), P],
     "spyr_conv2d_epilogue": [C.POINTER(ConvDesc), P, P],
     "spyr_conv2d_wgrad": [C.POINTER(WgradDesc), P],
+    "spyr_conv2d_wgrad_deferred": [C.POINTER(WgradDesc), C.POINTER(ReduceEntry), P],
+    "spyr_colsum_deferred": [P, c_ll, c_int, P, P, P, P, C.POINTER(ReduceEntry), P],
+    "spyr_stencil_wgrad_deferred": [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, C.POINTER(ReduceEntry), P],
+    "spyr_reduce_batched": [C.POINTER(ReduceEntry), c_int, P],
     "spyr_im2col3x3": [P, c_int, c_int, c_int, P, P, P, P],
     "spyr_col2im3x3": [P, c_int, c_int, c_int, P, P, c_int, P],
     "spyr_img_avgpool_pad8": [P, c_int, c_int, c_int, P, P],

@@ -431,8 +431,9 @@ __device__ __forceinline__ float spyr_warp_tree(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-static __global__ void spyr_sum_partials_kernel(const float* __restrict__ scratch, int nb, int n, SumSink sk) {
-  const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+__device__ __forceinline__ void spyr_sum_partials_body(const float* __restrict__ scratch, int nb, int n, const SumSink& sk,
+                                                       long long block) {
+  const int i = (int)((block * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
   float s = 0.f;
@@ -449,6 +450,9 @@ static __global__ void spyr_sum_partials_kernel(const float* __restrict__ scratc
     if (i < sk.split) sk.out0[i] += s;
     else sk.out1[i - sk.split] += s;
   }
+}
+static __global__ void spyr_sum_partials_kernel(const float* __restrict__ scratch, int nb, int n, SumSink sk) {
+  spyr_sum_partials_body(scratch, nb, n, sk, (long long)blockIdx.x);
 }
 static inline cudaError_t spyr_launch_sum_partials(const float* scratch, int nb, int n, const SumSink& sk, cudaStream_t st) {
   spyr_sum_partials_kernel<<<(n + 7) / 8, 256, 0, st>>>(scratch, nb, n, sk);

@@ -525,14 +525,15 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
 // the problem shape only) adjacent threads share one float4 of dw: each adds the slices lane, lane + lanes, ... and a fixed
 // xor tree combines them, so the order of the additions -- and the result, bit for bit -- does not depend on scheduling.
 // Rows ci >= Cin of a strided dw (the mask-channel row of cat(feature*mask, mask)) belong to another kernel: untouched.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nslices, int nimg, float* __restrict__ dw,
-                                    int taps, int Cin, int cin_stride, int Cout, int lanes) {
+__device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ partial, int nslices, int nimg,
+                                                  float* __restrict__ dw, int taps, int Cin, int cin_stride, int Cout,
+                                                  int lanes, long long block) {
   const int c4 = Cout >> 2;
   const long long per_img = (long long)taps * Cin * c4;
   const long long total = per_img * nimg;
   const size_t slice_floats = (size_t)taps * cin_stride * Cout;
   const int lane = (int)(threadIdx.x % (unsigned)lanes);
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const long long i = (block * blockDim.x + threadIdx.x) / lanes;
   const bool live = i < total;  // whole lane groups are live or not: the shuffles below stay within a group
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   size_t off = 0;
@@ -559,6 +560,30 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nslic
     float4 d = *reinterpret_cast<float4*>(dw + off);
     d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
     *reinterpret_cast<float4*>(dw + off) = d;
+  }
+}
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nslices, int nimg, float* __restrict__ dw,
+                                    int taps, int Cin, int cin_stride, int Cout, int lanes, int) {
+  wgrad_reduce_body(partial, nslices, nimg, dw, taps, Cin, cin_stride, Cout, lanes, (long long)blockIdx.x);
+}
+
+// Up to SPYR_REDUCE_BATCH pending second stages in one launch: block ranges per entry, same code per entry as the
+// immediate kernels (wgrad_reduce_kernel / spyr_sum_partials_kernel), so the results are bit-identical.
+struct ReduceBatch {
+  spyr_reduce_entry e[SPYR_REDUCE_BATCH];
+  int block0[SPYR_REDUCE_BATCH + 1];
+  int n;
+};
+__global__ void reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+  int k = 0;
+  while (k + 1 < b.n && (int)blockIdx.x >= b.block0[k + 1]) ++k;
+  const spyr_reduce_entry& e = b.e[k];
+  const long long block = (long long)blockIdx.x - b.block0[k];
+  if (e.kind == 1) {
+    wgrad_reduce_body(e.partial, e.nslices, e.nimg, e.out0, e.taps, e.rows, e.cin_stride, e.Cout, e.lanes, block);
+  } else {
+    SumSink sk = {e.out0, e.out1, e.out2, e.mode, e.C, e.sink_stride, e.sink_row, e.split};
+    spyr_sum_partials_body(e.partial, e.nb, e.n, sk, block);
   }
 }
 
@@ -871,8 +896,18 @@ extern "C" long long spyr_conv2d_wgrad_scratch_floats(const spyr_wgrad_desc* d) 
   return (long long)slices * (d->per_image ? d->B : 1) * d->ksize * d->ksize * cs * d->Cout;
 }
 
+static int wgrad_impl(const spyr_wgrad_desc* d, spyr_reduce_entry* deferred, cudaStream_t stream);
+
 extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+  return wgrad_impl(d, nullptr, (cudaStream_t)stream_);
+}
+extern "C" int spyr_conv2d_wgrad_deferred(const spyr_wgrad_desc* d, spyr_reduce_entry* out, void* stream_) {
+  SPYR_REQUIRE(out != nullptr, "conv2d_wgrad_deferred: out is NULL");
+  memset(out, 0, sizeof(*out));
+  return wgrad_impl(d, out, (cudaStream_t)stream_);
+}
+
+static int wgrad_impl(const spyr_wgrad_desc* d, spyr_reduce_entry* deferred, cudaStream_t stream) {
   int route = 0, slices = 0;
   const int rc0 = wgrad_route(d, &route, &slices);
   if (rc0) return rc0;
@@ -899,11 +934,50 @@ extern "C" int spyr_conv2d_wgrad(const spyr_wgrad_desc* d, void* stream_) {
     const long long total = (long long)nimg * d->ksize * d->ksize * rows * (d->Cout / 4);
     int lanes = 1;  // threads per output vector: enough parallelism for small gradients with many slices
     while (lanes < 32 && lanes < slices && total * lanes < 131072) lanes *= 2;
+    if (deferred != nullptr) {
+      // the caller batches this sum with the others of its backward pass (spyr_reduce_batched)
+      deferred->kind = 1;
+      deferred->partial = partial;
+      deferred->out0 = d->dw;
+      deferred->nslices = slices; deferred->nimg = nimg; deferred->taps = d->ksize * d->ksize; deferred->rows = rows;
+      deferred->cin_stride = cs; deferred->Cout = d->Cout; deferred->lanes = lanes;
+      return 0;
+    }
     const long long blocks = (total * lanes + 255) / 256;
     wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, slices, nimg, d->dw, d->ksize * d->ksize, rows, cs,
-                                                        d->Cout, lanes);
+                                                        d->Cout, lanes, 0);
     spyr_count_launch();
     SPYR_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int spyr_reduce_batched(const spyr_reduce_entry* entries, int n, void* stream) {
+  SPYR_REQUIRE(entries != nullptr && n >= 1 && n <= SPYR_REDUCE_BATCH, "reduce_batched: n=%d out of range", n);
+  ReduceBatch b;
+  memset(&b, 0, sizeof(b));
+  int blocks = 0, m = 0;
+  for (int i = 0; i < n; ++i) {
+    const spyr_reduce_entry& e = entries[i];
+    if (e.kind == 0) continue;
+    long long nb;
+    if (e.kind == 1) {
+      const long long total = (long long)e.nimg * e.taps * e.rows * (e.Cout / 4);
+      nb = (total * e.lanes + 255) / 256;
+    } else {
+      SPYR_REQUIRE(e.kind == 2, "reduce_batched: entry %d has kind %d", i, e.kind);
+      nb = (e.n + 7) / 8;
+    }
+    b.e[m] = e;
+    b.block0[m] = blocks;
+    blocks += (int)nb;
+    ++m;
+  }
+  if (m == 0) return 0;
+  b.block0[m] = blocks;
+  b.n = m;
+  reduce_batched_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b);
+  spyr_count_launch();
+  SPYR_LAUNCH_CHECK();
   return 0;
 }

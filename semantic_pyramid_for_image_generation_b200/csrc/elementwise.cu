@@ -973,8 +973,27 @@ extern "C" int spyr_gamma_residual_bwd(const void* g, const void* t, const float
   SPYR_LAUNCH_CHECK();
   return 0;
 }
+static int colsum_impl(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* scratch,
+                       spyr_reduce_entry* deferred, void* stream);
 extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* scratch,
                            void* stream) {
+  return colsum_impl(g, rows, C, out0, out1, out2, scratch, nullptr, stream);
+}
+extern "C" int spyr_colsum_deferred(const void* g, long long rows, int C, float* out0, float* out1, float* out2,
+                                    void* scratch, spyr_reduce_entry* out, void* stream) {
+  SPYR_REQUIRE(out != nullptr, "colsum_deferred: out is NULL");
+  memset(out, 0, sizeof(*out));
+  return colsum_impl(g, rows, C, out0, out1, out2, scratch, out, stream);
+}
+static void defer_sum(spyr_reduce_entry* e, const float* scratch, int nb, int n, const SumSink& sk) {
+  e->kind = 2;
+  e->partial = scratch;
+  e->out0 = sk.out0; e->out1 = sk.out1; e->out2 = sk.out2;
+  e->nb = nb; e->n = n; e->mode = sk.mode; e->C = sk.C; e->sink_stride = sk.cin_stride; e->sink_row = sk.ci_row;
+  e->split = sk.split;
+}
+static int colsum_impl(const void* g, long long rows, int C, float* out0, float* out1, float* out2, void* scratch,
+                       spyr_reduce_entry* deferred, void* stream) {
   SPYR_REQUIRE(scratch != nullptr, "colsum: scratch is NULL");
   SPYR_C8(C);
   const int cg = C / 8;
@@ -988,13 +1007,30 @@ extern "C" int spyr_colsum(const void* g, long long rows, int C, float* out0, fl
                                                                                 (float*)scratch));
   spyr_count_launch();
   SumSink sk = {out0, out1, out2, 0, C, 0, 0, 0};
+  if (deferred != nullptr) {
+    defer_sum(deferred, (const float*)scratch, grid, C, sk);
+    SPYR_LAUNCH_CHECK();
+    return 0;
+  }
   SPYR_CHECK_CUDA(spyr_launch_sum_partials((const float*)scratch, grid, C, sk, (cudaStream_t)stream));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();
   return 0;
 }
+static int stencil_impl(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride, int ci_row,
+                        void* scratch, spyr_reduce_entry* deferred, void* stream);
 extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride,
                                   int ci_row, void* scratch, void* stream) {
+  return stencil_impl(mask, g, B, H, W, C, dw, cin_stride, ci_row, scratch, nullptr, stream);
+}
+extern "C" int spyr_stencil_wgrad_deferred(const float* mask, const void* g, int B, int H, int W, int C, float* dw,
+                                           int cin_stride, int ci_row, void* scratch, spyr_reduce_entry* out, void* stream) {
+  SPYR_REQUIRE(out != nullptr, "stencil_wgrad_deferred: out is NULL");
+  memset(out, 0, sizeof(*out));
+  return stencil_impl(mask, g, B, H, W, C, dw, cin_stride, ci_row, scratch, out, stream);
+}
+static int stencil_impl(const float* mask, const void* g, int B, int H, int W, int C, float* dw, int cin_stride, int ci_row,
+                        void* scratch, spyr_reduce_entry* deferred, void* stream) {
   SPYR_REQUIRE(scratch != nullptr, "stencil_wgrad: scratch is NULL");
   SPYR_C8(C);
   const int cg = C / 8;
@@ -1016,6 +1052,11 @@ extern "C" int spyr_stencil_wgrad(const float* mask, const void* g, int B, int H
                                                                       (float*)scratch));
   spyr_count_launch();
   SumSink sk = {dw, nullptr, nullptr, 1, C, cin_stride, ci_row, 0};
+  if (deferred != nullptr) {
+    defer_sum(deferred, (const float*)scratch, grid, 9 * C, sk);
+    SPYR_LAUNCH_CHECK();
+    return 0;
+  }
   SPYR_CHECK_CUDA(spyr_launch_sum_partials((const float*)scratch, grid, 9 * C, sk, (cudaStream_t)stream));
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();

@@ -331,6 +331,7 @@ def generator_backward(G, ctx, g_img):
     gw = torch.zeros(sn.gw_floats, dtype=F32, device=dev)
     g_img = _f32c(g_img)
     ops.LEAF.begin(dev)  # weight/bias-gradient kernels from here on overlap the input-gradient chain
+    ops.DEFER.begin()    # ... and their fixed-order second stages are batched into one launch at the end
     x, mr, a, a3, img = ctx["xf"], ctx["mr"], ctx["a"], ctx["a3"], ctx["img"]
     B, H, W, c5 = x.shape
     f3, f5_ = G.final_block[3], G.final_block[5]
@@ -390,6 +391,7 @@ def generator_backward(G, ctx, g_img):
     g_h0 = ops.linear_bwd_x(g_h1, m1.weight_orig, st.sigma("linear_block_1.main_block.1"), x=h0, in_slope=LRELU)
     ops.linear_bwd_w(g_h0, ctx["z"], sn.gw_ptr(gw, "linear_layer"), ga.ptr(grad, G.linear_layer.bias))
     ops.LEAF.join()
+    ops.DEFER.flush()
     sn.backward(st, gw, grad)
     return grad
 
@@ -507,6 +509,7 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
     gw = torch.zeros(sn.gw_floats, dtype=F32, device=dev)
     if want_wgrad:
         ops.LEAF.begin(dev)
+        ops.DEFER.begin()
     feat0, feat, x7 = ctx["feat0"], ctx["feat"], ctx["x7"]
     E = feat.shape[1]
     l11 = D.layers[11]
@@ -557,6 +560,7 @@ def discriminator_backward(D, ctx, g_out, want_wgrad, want_input_grad):
         call("spyr_img_avgpool_pad8_bwd", g8.data_ptr(), B, H, W, g_img.data_ptr(), 1)
     if want_wgrad:
         ops.LEAF.join()
+        ops.DEFER.flush()
         sn.backward(st, gw, grad)
         return grad, g_img
     return None, g_img

@@ -165,6 +165,46 @@ class LeafStream(object):
 LEAF = LeafStream()
 
 
+class DeferredReductions(object):
+    """Second stages (fixed-order sums of partial results) of the weight / bias gradients of ONE backward pass, batched.
+
+    Between `begin()` and `flush()`, `wgrad`, `colsum` and `stencil_wgrad` launch only their first stage and leave a
+    description of the pending sum here; `flush()` (after the leaf stream has joined) performs all of them in one launch per
+    32 entries instead of ~90 small kernels.  Same arithmetic in the same order as the immediate form: bit-identical.
+    SPYR_DEFER_REDUCE=0 disables it."""
+
+    def __init__(self):
+        self.enabled = os.environ.get("SPYR_DEFER_REDUCE", "1") != "0"
+        self.entries = None
+        self.keep = []
+
+    def begin(self):
+        if self.entries is not None:
+            self.flush()
+        if self.enabled and PROFILE is None:
+            self.entries = []
+
+    def active(self):
+        return self.entries is not None
+
+    def add(self, entry, *tensors):
+        if entry.kind != 0:
+            self.entries.append(entry)
+        self.keep.extend(t for t in tensors if t is not None)
+
+    def flush(self):
+        entries, self.entries = self.entries, None
+        if entries:
+            for i in range(0, len(entries), N.REDUCE_BATCH):
+                chunk = entries[i:i + N.REDUCE_BATCH]
+                arr = (N.ReduceEntry * len(chunk))(*chunk)
+                call("spyr_reduce_batched", arr, len(chunk))
+        del self.keep[:]
+
+
+DEFER = DeferredReductions()
+
+
 def empty_bf16(*shape, device=None):
     return act_empty(shape, device or "cuda")
 
@@ -296,6 +336,10 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
     if PROFILE is None:
         if per_image:
             call("spyr_conv2d_wgrad", C.byref(d))  # attention dK / dV feed the rest of the backward: not a leaf
+        elif DEFER.active():
+            entry = N.ReduceEntry()
+            LEAF.run((x, dy, sc), "spyr_conv2d_wgrad_deferred", C.byref(d), C.byref(entry))
+            DEFER.add(entry, sc)
         else:
             LEAF.run((x, dy, sc), "spyr_conv2d_wgrad", C.byref(d))
     else:
@@ -308,12 +352,23 @@ def wgrad(x, dy, dw_ptr, B, H, W, Cin, Cout, ksize, cin_stride=0, per_image=Fals
 def colsum(g, C_, out0, out1=None, out2=None):
     rows = g.numel() // C_
     sc = scratch(C_, g.device)
+    if DEFER.active():
+        entry = N.ReduceEntry()
+        LEAF.run((g, sc), "spyr_colsum_deferred", g.data_ptr(), rows, C_, out0, out1, out2, sc.data_ptr(), C.byref(entry))
+        DEFER.add(entry, sc)
+        return
     LEAF.run((g, sc), "spyr_colsum", g.data_ptr(), rows, C_, out0, out1, out2, sc.data_ptr())
 
 
 def stencil_wgrad(mask, dy, B, H, W, Cout, gw_ptr, cin_stride, cin_index):
     """Weight gradient of the mask channel of cat(feature*mask, mask) (models.py:94): nine masked sums of dy."""
     sc = scratch(9 * Cout, dy.device)
+    if DEFER.active():
+        entry = N.ReduceEntry()
+        LEAF.run((mask, dy, sc), "spyr_stencil_wgrad_deferred", mask.data_ptr(), dy.data_ptr(), B, H, W, Cout, gw_ptr,
+                 cin_stride, cin_index, sc.data_ptr(), C.byref(entry))
+        DEFER.add(entry, sc)
+        return
     LEAF.run((mask, dy, sc), "spyr_stencil_wgrad", mask.data_ptr(), dy.data_ptr(), B, H, W, Cout, gw_ptr, cin_stride,
              cin_index, sc.data_ptr())
 
