@@ -797,7 +797,13 @@ static int wgrad_tc_plan(const spyr_wgrad_desc* d, WgradParams* pp) {
   const int ntiles = ceil_div(d->Cout, bn);
   int splits = d->splits;
   if (splits <= 0) {
-    splits = (2 * 148) / (mtiles * ntiles);
+    // Every split beyond the first costs a full FP32 copy of the gradient (its slice of partial sums is written, then read
+    // by the fixed-order reduction): split only while each CTA keeps >= 16 pixel tiles of reduction and the grid stays
+    // within one wave.  (With the round-1 rule, two waves of 4-5 k-step CTAs, the 8x8 / 16x16 layers spent 3/4 of their
+    // time moving partial sums.)
+    splits = 148 / (mtiles * ntiles);
+    const int by_work = p.ptiles / 16;
+    if (splits > by_work) splits = by_work;
     if (splits < 1) splits = 1;
   }
   if (splits > p.ptiles) splits = p.ptiles;
