@@ -527,13 +527,36 @@ def run_forward_config(args, rank, world, local_rank, device, wrapper, G, V, red
     reducer.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        s_images.copy_(h_images, non_blocking=True)
-        s_labels.copy_(h_labels, non_blocking=True)
-        for dm, hm in zip(s_masks, h_masks):
+    # every step's inputs cross PCIe from pinned memory inside the timed region: step 0's on the timed stream, step i+1's on
+    # a copy stream into staging buffers while step i computes, then device-to-device into the graph's inputs
+    stage = (torch.empty_like(s_images), torch.empty_like(s_labels), [torch.empty_like(m) for m in s_masks])
+    copy_stream = torch.cuda.Stream()
+    staged, consumed = torch.cuda.Event(), torch.cuda.Event()
+    main = torch.cuda.current_stream()
+
+    def load(images, labels, masks):
+        s_images.copy_(images, non_blocking=True)
+        s_labels.copy_(labels, non_blocking=True)
+        for dm, hm in zip(s_masks, masks):
             dm.copy_(hm, non_blocking=True)
         labels_f.copy_(s_labels)
+
+    t0.record()
+    load(h_images, h_labels, h_masks)
+    consumed.record(main)
+    for i in range(args.steps):
+        if i > 0:
+            main.wait_event(staged)
+            load(*stage)
+            consumed.record(main)
+        if i + 1 < args.steps:
+            copy_stream.wait_event(consumed)
+            with torch.cuda.stream(copy_stream):
+                stage[0].copy_(h_images, non_blocking=True)
+                stage[1].copy_(h_labels, non_blocking=True)
+                for dm, hm in zip(stage[2], h_masks):
+                    dm.copy_(hm, non_blocking=True)
+                staged.record(copy_stream)
         step()
         result_host.copy_(img.abs().mean().reshape(1), non_blocking=True)
     t1.record()

@@ -24,8 +24,8 @@ static thread_local int g_last_kernel = -1;
 void spyr_note_kernel(int id) { g_last_kernel = id; }
 extern "C" const char* spyr_last_conv_kernel(void) {
   static const char* names[] = {"conv_halo2_kernel", "conv_halo_kernel", "conv_fprop_kernel", "wgrad_halo_kernel",
-                                "conv_wgrad_kernel"};
-  return (g_last_kernel >= 0 && g_last_kernel < 5) ? names[g_last_kernel] : "";
+                                "conv_wgrad_kernel", "conv_stack3_kernel"};
+  return (g_last_kernel >= 0 && g_last_kernel < 6) ? names[g_last_kernel] : "";
 }
 
 extern "C" const char* spyr_last_error(void) { return g_err; }

@@ -97,12 +97,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
       bool load_b = true;  // resident weights: only the first tile of this CTA loads them
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-        const int w0 = (m_tile % p.tiles_w) * 8;
-        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
-        const int n0 = m_tile / (p.tiles_w * p.tiles_h);
-        const int n_off = n_tile * p.block_n;
+      HaloTileIter ti;
+      ti.init(blockIdx.x, p.m_tiles);
+      for (; ti.nt < p.n_tiles; ti.next(gridDim.x, p.m_tiles)) {
+        int w0, h0, n0;
+        halo_tile_origin(p, ti.m, th_rows, w0, h0, n0);
+        const int n_off = ti.nt * p.block_n;
         for (int s = 0; s < p.nsrc; ++s) {
           const int bd = p.border[s];
           const int taps = bd ? 9 : 1;
@@ -235,14 +235,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     es.stage = smem_u32(epi_stage) + (uint32_t)((warp - 4) * 2 * EPI_STAGE_BYTES);
     es.lane = lane;
     es.sbuf = &sbuf;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    HaloTileIter ti;
+    ti.init(blockIdx.x, p.m_tiles);
+    for (; ti.nt < p.n_tiles; ti.next(gridDim.x, p.m_tiles), ++it) {
       const int buf = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-      const int w0 = (m_tile % p.tiles_w) * 8;
-      const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
-      const int n = m_tile / (p.tiles_w * p.tiles_h);
-      const int n_off = n_tile * p.block_n;
+      int w0, h0, n;
+      halo_tile_origin(p, ti.m, th_rows, w0, h0, n);
+      const int n_off = ti.nt * p.block_n;
       if (n_off != staged_n_off) {
         // new N block: stage its constants into the other buffer, then one barrier among the 8 epilogue warps.  Warps
         // reach this barrier only after finishing the previous tile, so the buffer being overwritten is no longer read.
@@ -365,6 +365,9 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   if (p.tmem_cols > 512) return -1;
   p.tiles_w = d->W / 8;
   p.tiles_h = d->H / (16 * p.msub);
+  if ((p.tiles_w & (p.tiles_w - 1)) != 0 || (p.tiles_h & (p.tiles_h - 1)) != 0) return -1;  // shift / mask tile decode
+  for (p.lw = 0; (1 << p.lw) < p.tiles_w; ++p.lw) {}
+  for (p.lh = 0; (1 << p.lh) < p.tiles_h; ++p.lh) {}
   p.m_tiles = p.tiles_w * p.tiles_h * d->B;
   p.n_tiles = ceil_div(d->Cout, bn);
   p.total_tiles = p.m_tiles * p.n_tiles;

@@ -151,13 +151,12 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       const bool issue = elect_one();
       int abuf = 0, bst = 0;
       uint32_t aph = 0, bph = 0;
-      for (int t = pair; t < total_pairs; t += num_pairs) {
-        const int pm = t % (p.m_tiles >> 1), n_tile = t / (p.m_tiles >> 1);
-        const int m_tile = 2 * pm + (int)rank;
-        const int w0 = (m_tile % p.tiles_w) * 8;
-        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
-        const int n0 = m_tile / (p.tiles_w * p.tiles_h);
-        const int n_off = n_tile * p.block_n + (int)rank * half_n;
+      HaloTileIter ti;
+      ti.init(pair, p.m_tiles >> 1);
+      for (; ti.nt < p.n_tiles; ti.next(num_pairs, p.m_tiles >> 1)) {
+        int w0, h0, n0;
+        halo_tile_origin(p, 2 * ti.m + (int)rank, th_rows, w0, h0, n0);
+        const int n_off = ti.nt * p.block_n + (int)rank * half_n;
         for (int s = 0; s < p.nsrc; ++s) {
           const int bd = p.border[s];
           const int taps = bd ? 9 : 1;
@@ -281,15 +280,14 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
     es.lane = lane;
     es.sbuf = &sbuf;
     es.w = es.h = es.n = 0;
-    for (int t = pair; t < total_pairs; t += num_pairs, ++it) {
+    HaloTileIter ti;
+    ti.init(pair, p.m_tiles >> 1);
+    for (; ti.nt < p.n_tiles; ti.next(num_pairs, p.m_tiles >> 1), ++it) {
       const int buf = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const int pm = t % (p.m_tiles >> 1), n_tile = t / (p.m_tiles >> 1);
-      const int m_tile = 2 * pm + (int)rank;
-      const int w0 = (m_tile % p.tiles_w) * 8;
-      const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * th_rows;
-      const int n = m_tile / (p.tiles_w * p.tiles_h);
-      const int n_off = n_tile * p.block_n;
+      int w0, h0, n;
+      halo_tile_origin(p, 2 * ti.m + (int)rank, th_rows, w0, h0, n);
+      const int n_off = ti.nt * p.block_n;
       if (n_off != staged_n_off) {
         cbuf ^= 1;
         float* dst = epi_const + cbuf * 11 * p.block_n;
@@ -410,6 +408,9 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   if (p.tmem_cols > 512) return -1;
   p.tiles_w = d->W / 8;
   p.tiles_h = d->H / (16 * p.msub);
+  if ((p.tiles_w & (p.tiles_w - 1)) != 0 || (p.tiles_h & (p.tiles_h - 1)) != 0) return -1;  // shift / mask tile decode
+  for (p.lw = 0; (1 << p.lw) < p.tiles_w; ++p.lw) {}
+  for (p.lh = 0; (1 << p.lh) < p.tiles_h; ++p.lh) {}
   p.m_tiles = p.tiles_w * p.tiles_h * d->B;
   if (p.m_tiles & 1) return -1;
   p.n_tiles = d->Cout / bn;

@@ -28,6 +28,10 @@ struct HaloParams {
   int res_pooled;  // residual lives at (H/2, W/2) and is added as 0.25 * residual[h/2][w/2]
   int tma_store;   // epilogue writes y_raw / y_act through shared-memory staging + TMA stores (maps.y)
   int b_resident;  // conv_halo.cu: every (source, chunk, tap) weight slice of the layer stays in shared memory
+  int dbg;         // developer switches of conv_stack3.cu (SPYR_S3_DBG), 0 in production
+  int tma_in;      // conv_stack3.cu: bit 0 = gate, bit 1 = residual arrive through TMA loads into shared memory (maps.g)
+  int lw, lh;      // log2(tiles_w), log2(tiles_h) of the halo kernels (H, W are powers of two there)
+  int step_w, step_h, step_n;  // gridDim.x decomposed over (tiles_w, tiles_h, images): TileIter advances without divisions
   int split;       // split-BF16 mode: y_raw / y_act / residual are hi + lo plane pairs (generic epilogue only)
   long long y_plane, res_plane;  // elements from the hi to the lo plane of the outputs / of the residual
   float acc_scale;  // split mode: 1 + (hi*hi accumulations per output) * 2^-25 -- the tensor pipe's FP32 accumulator truncates
@@ -52,7 +56,54 @@ struct HaloMaps {
   CUtensorMap x[SPYR_CONV_MAX_SRC];
   CUtensorMap w[SPYR_CONV_MAX_SRC];
   CUtensorMap y[2];  // y_raw, y_act as (C, W, H, B) with a (32 ch, 8, 4, 1) box, SWIZZLE_64B: epilogue TMA stores
+  CUtensorMap g[2];  // conv_stack3.cu: gate (dmask) and residual maps, same box as its y maps: epilogue TMA loads
 };
+
+// Coordinates of the tiles a persistent CTA visits (tile = blockIdx.x, += gridDim.x), kept as (column tile, row tile,
+// image) and advanced with two compare-and-subtract carries.  The three runtime divisions of tile -> (tw, th, n) cost
+// ~130 dependent instructions (IABS / I2F / MUFU.RCP / IMAD.HI chains) per tile in EVERY role; the epilogue warps, two per
+// scheduler and latency-bound, spent a quarter of their per-tile time on them (profiles/r02_ncu_conv_stack3.txt).
+struct TileIter {
+  int tw, th, n;
+  __device__ __forceinline__ void init(const HaloParams& p, int tile) {
+    tw = tile % p.tiles_w;
+    const int r = tile / p.tiles_w;
+    th = r % p.tiles_h;
+    n = r / p.tiles_h;
+  }
+  __device__ __forceinline__ void next(const HaloParams& p) {
+    tw += p.step_w;
+    const int cw = tw >= p.tiles_w ? 1 : 0;
+    tw -= cw ? p.tiles_w : 0;
+    th += p.step_h + cw;
+    const int ch = th >= p.tiles_h ? 1 : 0;
+    th -= ch ? p.tiles_h : 0;
+    n += p.step_n + ch;
+  }
+};
+
+// conv_halo.cu / conv_halo2.cu: persistent loop over work items t = n_tile * M + m (t = first, += step) without the five
+// runtime divisions of t -> (n_tile, m) -> (column tile, row tile, image): (m, n_tile) advance by compare-and-subtract,
+// the pixel tile decodes with shifts because tiles_w and tiles_h are powers of two.
+struct HaloTileIter {
+  int m, nt;
+  __device__ __forceinline__ void init(int first, int M) {
+    nt = first / M;
+    m = first - nt * M;
+  }
+  __device__ __forceinline__ void next(int step, int M) {
+    m += step;
+    while (m >= M) {
+      m -= M;
+      ++nt;
+    }
+  }
+};
+__device__ __forceinline__ void halo_tile_origin(const HaloParams& p, int m_tile, int th_rows, int& w0, int& h0, int& n0) {
+  w0 = (m_tile & (p.tiles_w - 1)) * 8;
+  h0 = ((m_tile >> p.lw) & (p.tiles_h - 1)) * th_rows;
+  n0 = m_tile >> (p.lw + p.lh);
+}
 
 constexpr int EPI_STAGE_BYTES = 2048;  // one warp's 32 pixels x 32 channels BF16
 constexpr int EPI_STAGE_TOTAL = EPI_WARPS * 2 * EPI_STAGE_BYTES;
@@ -278,6 +329,10 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+
+__device__ __forceinline__ void lds128u(uint32_t addr, uint32_t* v) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 }
 
 template <int OUT, bool DMASK, bool RES>

@@ -22,6 +22,7 @@ extern void spyr_count_launch();
 void spyr_note_kernel(int id);
 int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream);
 int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream);
+int spyr_conv_stack3_launch(const spyr_conv_desc* d, cudaStream_t stream);
 int spyr_wgrad_halo_launch(const spyr_wgrad_desc* d, cudaStream_t stream);
 
 namespace {
@@ -653,6 +654,11 @@ static int conv2d_fprop_impl(const spyr_conv_desc* d, cudaStream_t stream) {
     static const bool legacy = getenv("SPYR_CONV_LEGACY") != nullptr;
     static const bool no_pair = getenv("SPYR_CONV_NO_PAIR") != nullptr;
     if (!legacy) {
+      {
+        // 64 output channels, 3x3, maps >= 128 wide: the three taps of a kernel row stacked along N (conv_stack3.cu)
+        const int rc3 = spyr_conv_stack3_launch(d, stream);
+        if (rc3 >= 0) return rc3;
+      }
       if (!no_pair) {
         // >= 128 output channels: CTA pairs (tcgen05 cta_group::2) halve the weight operand fetched per SM
         const int rc2 = spyr_conv_halo2_launch(d, stream);

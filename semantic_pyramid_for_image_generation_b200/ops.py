@@ -113,6 +113,11 @@ def _profiled(kernel, flops, nbytes, name, desc, label=""):
     PROFILE.append((real, flops, nbytes, e0, e1, label))
 
 
+def last_conv_kernel():
+    """Name of the tensor-core kernel the last conv / wgrad call of this thread launched (spyr_last_conv_kernel)."""
+    return N.lib().spyr_last_conv_kernel().decode()
+
+
 class LeafStream(object):
     """Second CUDA stream for the leaves of a backward pass.
 

@@ -400,6 +400,12 @@ int main(int argc, char** argv) {
     fails += test_fprop(3, 128, 128, 64, 64, 3, 1, false, 0, 0);
     fails += test_fprop(3, 128, 128, 32, 64, 1, 1, true, 0, 0);
     fails += test_fprop(3, 128, 128, 64, 64, 3, 2, true, 0, 0);
+    // conv_stack3.cu (Cout = 64, 3x3, W >= 128): ragged last column tile, 2-chunk and partial-chunk sources, 4-row map
+    fails += test_fprop(2, 256, 256, 64, 64, 3, 1, true, 0, 0);
+    fails += test_fprop(2, 128, 128, 128, 64, 3, 1, true, 0, 0);
+    fails += test_fprop(1, 128, 128, 32, 64, 3, 1, false, 0, 0);
+    fails += test_fprop(2, 4, 128, 64, 64, 3, 2, true, 0, 0);
+    fails += test_fprop(1, 64, 256, 192, 64, 3, 1, false, 0, 0);
   }
   if (!strcmp(mode, "all") || !strcmp(mode, "wgrad")) {
     fails += test_wgrad(2, 16, 16, 64, 64, 3, 0, 0, 1);

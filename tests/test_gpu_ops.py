@@ -617,6 +617,37 @@ def test_conv_with_pooled_residual(ops):
     assert rel_l2(nchw(got), want) < tol16()
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 128, 128), (1, 128, 256, 256), (1, 32, 8, 128)])
+def test_conv_64_channel_rows_stacked(ops, shape):
+    """Cout = 64, 3x3, maps >= 128 wide run on conv_stack3.cu (the three taps of a kernel row stacked along N, outputs
+    combined across neighbouring lanes): plain, bias + activation, gated input gradient + residual, two sources, the
+    ragged last column tile (128 = 4 * 30 + 8, 256 = 8 * 30 + 16) and a partial 64-channel chunk (Cin = 32)."""
+    B, cin, H, W = shape
+    cout = 64
+    g = gen(31)
+    x = q(torch.randn(B, cin, H, W, generator=g))
+    x2 = q(torch.randn(B, 64, H, W, generator=g))
+    w = q(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    w2 = q(torch.randn(cout, 64, 3, 3, generator=g) / 24)
+    b = torch.randn(cout, generator=g)
+    gate = q(torch.randn(B, cout, H, W, generator=g))
+    res = q(torch.randn(B, cout, H, W, generator=g))
+    ref = F.conv2d(x, w, b, padding=1)
+    raw, act = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3)], bias=b.cuda(), want_raw=True, want_act=True)
+    assert ops.last_conv_kernel() == "conv_stack3_kernel"
+    assert rel_l2(nchw(raw), ref) < tol16()
+    assert rel_l2(nchw(act), F.leaky_relu(ref, 0.2)) < tol16()
+    ref2 = F.conv2d(x, w, None, padding=1) + F.conv2d(x2, w2, None, padding=1)
+    ref2 = torch.where(gate > 0, ref2, 0.2 * ref2) + res
+    got, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3), ops.Src(nhwc(x2), pack(w2), 64, 3)],
+                      dmask=nhwc(gate), dmask_slope=0.2, residual=nhwc(res))
+    assert ops.last_conv_kernel() == "conv_stack3_kernel"
+    assert rel_l2(nchw(got), ref2) < tol16()
+    again, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3), ops.Src(nhwc(x2), pack(w2), 64, 3)],
+                        dmask=nhwc(gate), dmask_slope=0.2, residual=nhwc(res))
+    assert torch.equal(ops.act_value(got), ops.act_value(again))
+
+
 def test_reductions_are_bit_reproducible(ops):
     """No floating-point atomics: split-K convolutions, weight gradients, bias column sums, BN statistics and the stencil
     gradient give bit-identical results on repeated launches (the small-map split-K and every weight gradient used
