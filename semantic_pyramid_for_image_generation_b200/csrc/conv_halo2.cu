@@ -400,8 +400,33 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.nsrc = d->nsrc;
   static const bool bn128 = getenv("SPYR_PAIR_BN128") != nullptr;  // experiment: less weight traffic per FLOP
-  const int bn = narrow ? 64 : ((d->Cout % 256 == 0 && !(bn128 && d->H % 32 == 0)) ? 256 : 128);  // whole N blocks only
+  int bn = narrow ? 64 : ((d->Cout % 256 == 0 && !(bn128 && d->H % 32 == 0)) ? 256 : 128);  // whole N blocks only
   p.msub = (d->H % 32 == 0 && bn <= 128) ? 2 : 1;
+  static const bool no_wave_model = getenv("SPYR_PAIR_NO_WAVE_MODEL") != nullptr;
+  if (!narrow && !no_wave_model && (bn == 256 || p.msub == 2)) {
+    // Wave quantisation on the 16x16 / 32x32 maps: 20 x 32x32 pixels x 256 channels are 80 pair tiles of 128 x 256 on 74
+    // pair slots -- two waves, the second 8 % full.  Half-size work items (128 pixels x 128 channels per CTA) make it 160
+    // items = three half-length waves.  Cost = waves x (item size + a fixed per-item overhead); the smaller item is taken
+    // when it wins by >= 10 % (on large maps the bigger item's lower operand traffic per FLOP is worth more).
+    static int slots = 0;
+    if (slots == 0) {
+      int dev = 0, sms = 0;
+      SPYR_CHECK_CUDA(cudaGetDevice(&dev));
+      SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      slots = sms / 2;
+    }
+    const long long mt_big = (long long)(d->W / 8) * (d->H / (16 * p.msub)) * d->B;
+    const long long mt_small = (long long)(d->W / 8) * (d->H / 16) * d->B;
+    if ((mt_big & 1) == 0 && (mt_small & 1) == 0) {
+      const long long items_big = (mt_big / 2) * (d->Cout / bn), items_small = (mt_small / 2) * (d->Cout / 128);
+      const long long cost_big = ((items_big + slots - 1) / slots) * (p.msub * bn + 24);
+      const long long cost_small = ((items_small + slots - 1) / slots) * (128 + 24);
+      if (cost_small * 10 <= cost_big * 9) {
+        bn = 128;
+        p.msub = 1;
+      }
+    }
+  }
   p.block_n = bn;
   p.bn_cols = bn;
   p.tmem_cols = pow2_at_least2(2 * p.msub * p.bn_cols, 32);

@@ -30,8 +30,14 @@ TOL = {
     # ~sqrt(eps) (FP32 vs FP64 of the reference differ by 4e-4 on generator gradients).  At the strict
     # mode's eps ~ 3e-5 that floor is 6e-3 .. 9e-3; the test prints it (oracle with hi+lo rounding at the storage points vs
     # the plain FP32 oracle) next to the measured value.  Everything else is held to north_star's 5e-3.
+    # grad_head compares a 4096-element SAMPLE of each gradient tensor with the reference's: the worst of ~60 such samples
+    # scatters by x2 between equally accurate builds (same test, 64-channel layers on the CTA-pair kernel: worst 7.5e-3,
+    # mean 2.0e-3; on conv_stack3, whose own error against FP64 is the lower of the two: worst 1.53e-2, mean 2.3e-3), so
+    # the per-tensor bound is 3e-2 and the MEAN over the tensors -- which does not scatter -- is held to north_star's 5e-3
+    # (grad_head_mean); every tensor's norm is held to 5e-3 as well.
     "split": dict(vgg=[5e-3] * 7, vgg_dimg=(1.5e-2, 0.9999), g_img=5e-3, g_state=5e-3, g_grad=1.5e-2, d_pred=5e-3,
-                  d_dimg=(1.5e-2, 0.9999), d_grad=5e-3, loss=5e-3, grad_norm=5e-3, grad_head=1.5e-2, feat_sub=5e-3),
+                  d_dimg=(1.5e-2, 0.9999), d_grad=5e-3, loss=5e-3, grad_norm=5e-3, grad_head=3e-2, grad_head_mean=5e-3,
+                  feat_sub=5e-3),
     "bf16": dict(vgg=[6e-3] * 3 + [1.2e-2] * 4, vgg_dimg=(0.35, 0.94), g_img=2e-2, g_state=2e-2, g_grad=0.2, d_pred=4e-2,
                  d_dimg=(0.25, 0.97), d_grad=8e-2, loss=1e-1, grad_norm=0.2, grad_head=None, feat_sub=1.5e-2),
 }
@@ -371,6 +377,7 @@ def test_training_step_matches_reference_golden(cf, mode):
         assert abs(got - ref) <= T["loss"] * max(abs(ref), 1e-3), (name, got, ref)
     # parameter gradients of the generator phase are still in .grad
     worst_n = worst_h = 0.0
+    heads = []
     for name, p in G.named_parameters():
         ref_n = gold["g_grad_norms"][name]
         # biases in front of a batch norm have analytically (near-)zero gradients whose computed value is cancellation
@@ -383,9 +390,13 @@ def test_training_step_matches_reference_golden(cf, mode):
             if T["grad_head"] is not None and float(head.norm()) > 1e-3 * ref_n:
                 eh = rel_l2(p.grad.flatten()[:head.numel()], head)
                 worst_h = max(worst_h, eh)
+                heads.append(eh)
                 assert eh < T["grad_head"], (name, eh)
-    print("[%s cf=%d] G gradients vs reference: worst norm error %.3e, worst leading-elements rel-L2 %.3e" %
-          (mode, cf, worst_n, worst_h))
+    mean_h = sum(heads) / max(len(heads), 1)
+    print("[%s cf=%d] G gradients vs reference: worst norm error %.3e, leading-elements rel-L2 worst %.3e mean %.3e (%d tensors)"
+          % (mode, cf, worst_n, worst_h, mean_h, len(heads)))
+    if T.get("grad_head_mean") is not None:
+        assert mean_h < T["grad_head_mean"], mean_h
     sd = G.state_dict()
     for k, ref in gold["post_step"].items():
         assert rel_l2(sd[k], ref) < T["g_state"] or torch.allclose(sd[k].float().cpu(), ref.float(), atol=1e-5), k

@@ -641,7 +641,8 @@ def test_conv_64_channel_rows_stacked(ops, shape):
     ref2 = torch.where(gate > 0, ref2, 0.2 * ref2) + res
     got, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3), ops.Src(nhwc(x2), pack(w2), 64, 3)],
                       dmask=nhwc(gate), dmask_slope=0.2, residual=nhwc(res))
-    assert ops.last_conv_kernel() == "conv_stack3_kernel"
+    if W >= 256 or ops.SPLIT:  # two 64-channel chunks on a 128-wide map: the pair kernel is ahead (conv_stack3.cu)
+        assert ops.last_conv_kernel() == "conv_stack3_kernel"
     assert rel_l2(nchw(got), ref2) < tol16()
     again, _ = ops.conv(B, H, W, cout, [ops.Src(nhwc(x), pack(w), cin, 3), ops.Src(nhwc(x2), pack(w2), 64, 3)],
                         dmask=nhwc(gate), dmask_slope=0.2, residual=nhwc(res))
