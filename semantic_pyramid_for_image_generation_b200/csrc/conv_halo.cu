@@ -33,7 +33,7 @@ void spyr_note_kernel(int id);
 namespace {
 using namespace halo;
 
-template <bool SPLIT>
+template <bool SPLIT, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -271,7 +271,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       const int w = w0 + (m & 7);
       float mk[2][9];
       int mk_mode[2] = {0, 0};
-      if (p.stencil_mask != nullptr) {
+      if (EPI == 0 && p.stencil_mask != nullptr) {
         for (int sub = 0; sub < p.msub; ++sub) {
           const int h = h0 + sub * 16 + (m >> 3);
           bool all0 = true, all1 = true;
@@ -313,7 +313,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_dispatch<SPLIT>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
+          epilogue_static<SPLIT, EPI>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
@@ -488,12 +488,6 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
                             (size_t)(p.tma_store ? EPI_STAGE_TOTAL : 0) +
                             (2 * p.a_bufs + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
   SPYR_REQUIRE(smem_bytes <= 227 * 1024, "conv2d_fprop: shared-memory plan of %zu bytes exceeds 227 KB", smem_bytes);
-  static bool configured = false;
-  if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -501,10 +495,15 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  if (p.split)
-    conv_halo_kernel<true><<<grid, THREADS, smem_bytes, stream>>>(maps, p);
-  else
-    conv_halo_kernel<false><<<grid, THREADS, smem_bytes, stream>>>(maps, p);
+  void (*kernel)(HaloMaps, HaloParams) = conv_halo_kernel<true, 0>;
+  const int epi_index = epi_static_index(p);
+  if (!p.split) { SPYR_EPI_SWITCH(epi_index, kernel = conv_halo_kernel<false, kEpi>) }
+  static bool configured[2][EPI_VARIANTS] = {};
+  if (!configured[p.split ? 1 : 0][epi_index]) {
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[p.split ? 1 : 0][epi_index] = true;
+  }
+  kernel<<<grid, THREADS, smem_bytes, stream>>>(maps, p);
   spyr_note_kernel(1);
   spyr_count_launch();
   SPYR_LAUNCH_CHECK();

@@ -87,7 +87,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -315,7 +315,7 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
       const int w = w0 + (m & 7);
       float mk[2][9];
       int mk_mode[2] = {0, 0};
-      if (p.stencil_mask != nullptr) {
+      if (EPI == 0 && p.stencil_mask != nullptr) {
         for (int sub = 0; sub < p.msub; ++sub) {
           const int h = h0 + sub * 16 + (m >> 3);
           bool all0 = true, all1 = true;
@@ -354,7 +354,7 @@ conv_halo2_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
           uint32_t r[32];
           tmem_ld32(acc + (uint32_t)c0, r);
           tmem_ld_wait();
-          epilogue_dispatch<SPLIT>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
+          epilogue_static<SPLIT, EPI>(p, r, pix, n_off + c0, c0, ec, mk[sub], mk_mode[sub], es);
         }
       }
       tc_fence_before();
@@ -519,11 +519,13 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   }
   const size_t smem_bytes = (size_t)A_BUFS * p.a_buf_bytes + (size_t)stages * p.b_stage_bytes +
                             (2 * A_BUFS + 2 * stages + 4) * 8 + 16 + (size_t)2 * 11 * bn * 4 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SPYR_CHECK_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  void (*kernel)(HaloMaps, HaloParams) = conv_halo2_kernel<true, 0>;
+  const int epi_index = epi_static_index(p);
+  if (!p.split) { SPYR_EPI_SWITCH(epi_index, kernel = conv_halo2_kernel<false, kEpi>) }
+  static bool configured[2][EPI_VARIANTS] = {};
+  if (!configured[p.split ? 1 : 0][epi_index]) {
+    SPYR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[p.split ? 1 : 0][epi_index] = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -547,10 +549,7 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (p.split)
-    SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel<true>, maps, p));
-  else
-    SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo2_kernel<false>, maps, p));
+  SPYR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, p));
   spyr_note_kernel(0);
   spyr_count_launch();
   return 0;

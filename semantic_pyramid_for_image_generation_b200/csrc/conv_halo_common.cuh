@@ -498,4 +498,62 @@ __device__ __forceinline__ void epilogue_dispatch(const HaloParams& p, const uin
   }
 }
 
+// ---- compile-time form of epilogue_dispatch ----
+// EPI: 0 = generic epilogue_chunk; 1..12 = HaloParams::epi_mode (epilogue_chunk_fast<OUT, DMASK, RES>); 13..18 = the pooled
+// epilogue, 13 + (OUT - 1) * 2 + RES.  One epilogue per kernel instantiation: the 19-way runtime switch kept every variant's
+// registers and code in one kernel (168 registers with spills; conv_stack3.cu measured 486 -> 336 instructions per tile
+// and chunk when its switch and its index divisions went away).
+constexpr int EPI_VARIANTS = 19;
+__host__ inline int epi_static_index(const HaloParams& p) {
+  if (p.split || p.epi_mode == 0) return 0;
+  if (p.pool) return 13 + ((p.epi_mode - 1) / 4) * 2 + ((p.epi_mode - 1) & 1);
+  return p.epi_mode;
+}
+
+template <bool SPLIT, int EPI>
+__device__ __forceinline__ void epilogue_static(const HaloParams& p, const uint32_t* r, size_t pix, int col0, int c0,
+                                                const EpiConst& ec, const float* mk, int mk_mode, const EpiStore& es) {
+  if (SPLIT || EPI == 0) {
+    epilogue_chunk<SPLIT>(p, r, pix, col0, c0, ec, mk, mk_mode, es);
+    return;
+  }
+  const uint32_t bs = smem_u32(ec.bias + c0);
+  if (EPI >= 13) {
+    constexpr int OUT = (EPI >= 13 ? (EPI - 13) / 2 : 0) + 1;
+    constexpr bool RES = ((EPI - 13) & 1) != 0;
+    const int w = (int)(pix % (size_t)p.W);
+    const size_t row = pix / (size_t)p.W;  // n*H + h
+    const size_t poff = ((row >> 1) * (size_t)(p.W >> 1) + (size_t)(w >> 1)) * p.Cout + col0;
+    epilogue_chunk_pool<OUT, RES>(p, r, poff, es.lane, bs);
+  } else {
+    constexpr int E = (EPI >= 1 && EPI <= 12) ? EPI : 1;
+    constexpr int OUT = (E - 1) / 4 + 1;
+    constexpr bool DMASK = ((E - 1) & 2) != 0;
+    constexpr bool RES = ((E - 1) & 1) != 0;
+    const size_t off0 = pix * p.Cout + col0;
+    size_t ro = off0;
+    float rsc = 1.f;
+    if (RES && p.res_pooled) {
+      const int w = (int)(pix % (size_t)p.W);
+      const size_t row = pix / (size_t)p.W;
+      ro = ((row >> 1) * (size_t)(p.W >> 1) + (size_t)(w >> 1)) * p.Cout + col0;
+      rsc = 0.25f;
+    }
+    epilogue_chunk_fast<OUT, DMASK, RES>(p, r, off0, col0, bs, es, ro, rsc);
+  }
+}
+
+// switch (index) with `kEpi` bound to the compile-time value in `body`
+#define SPYR_EPI_CASE(n, ...) case n: { constexpr int kEpi = n; __VA_ARGS__; } break;
+#define SPYR_EPI_SWITCH(index, ...)                                                                                  \
+  switch (index) {                                                                                                   \
+    SPYR_EPI_CASE(0, __VA_ARGS__) SPYR_EPI_CASE(1, __VA_ARGS__) SPYR_EPI_CASE(2, __VA_ARGS__)                        \
+    SPYR_EPI_CASE(3, __VA_ARGS__) SPYR_EPI_CASE(4, __VA_ARGS__) SPYR_EPI_CASE(5, __VA_ARGS__)                        \
+    SPYR_EPI_CASE(6, __VA_ARGS__) SPYR_EPI_CASE(7, __VA_ARGS__) SPYR_EPI_CASE(8, __VA_ARGS__)                        \
+    SPYR_EPI_CASE(9, __VA_ARGS__) SPYR_EPI_CASE(10, __VA_ARGS__) SPYR_EPI_CASE(11, __VA_ARGS__)                      \
+    SPYR_EPI_CASE(12, __VA_ARGS__) SPYR_EPI_CASE(13, __VA_ARGS__) SPYR_EPI_CASE(14, __VA_ARGS__)                     \
+    SPYR_EPI_CASE(15, __VA_ARGS__) SPYR_EPI_CASE(16, __VA_ARGS__) SPYR_EPI_CASE(17, __VA_ARGS__)                     \
+    default: { constexpr int kEpi = 18; __VA_ARGS__; } break;                                                        \
+  }
+
 }  // namespace halo
