@@ -392,6 +392,20 @@ def main():
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the five losses, every step ----
     loss_host = torch.empty(len(METRICS), dtype=torch.float32).pin_memory()
+    # untimed warm-up of the end-to-end path itself (first use of the copy stream, of the staging buffers and of the DMA
+    # mappings of the pinned batch: on a cold box these one-off costs were worth 4 ms/step over a 20-step region)
+    for i in range(max(args.warmup, 3)):
+        if captured is not None:
+            if i == 0:
+                captured.load(h_images, h_labels, h_masks)
+            out = captured()
+            if i + 1 < max(args.warmup, 3):
+                captured.prefetch(h_images, h_labels, h_masks)
+        else:
+            s_images.copy_(h_images, non_blocking=True)
+            out = eager_step()
+        loss_host.copy_(torch.stack([out[name] for name in METRICS]), non_blocking=True)
+    torch.cuda.synchronize()
     reducer.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -541,24 +555,29 @@ def run_forward_config(args, rank, world, local_rank, device, wrapper, G, V, red
             dm.copy_(hm, non_blocking=True)
         labels_f.copy_(s_labels)
 
+    def e2e_pass(steps):
+        load(h_images, h_labels, h_masks)
+        consumed.record(main)
+        for i in range(steps):
+            if i > 0:
+                main.wait_event(staged)
+                load(*stage)
+                consumed.record(main)
+            if i + 1 < steps:
+                copy_stream.wait_event(consumed)
+                with torch.cuda.stream(copy_stream):
+                    stage[0].copy_(h_images, non_blocking=True)
+                    stage[1].copy_(h_labels, non_blocking=True)
+                    for dm, hm in zip(stage[2], h_masks):
+                        dm.copy_(hm, non_blocking=True)
+                    staged.record(copy_stream)
+            step()
+            result_host.copy_(img.abs().mean().reshape(1), non_blocking=True)
+
+    e2e_pass(max(args.warmup, 3))  # untimed warm-up of the end-to-end path (copy stream, staging, DMA mappings)
+    torch.cuda.synchronize()
     t0.record()
-    load(h_images, h_labels, h_masks)
-    consumed.record(main)
-    for i in range(args.steps):
-        if i > 0:
-            main.wait_event(staged)
-            load(*stage)
-            consumed.record(main)
-        if i + 1 < args.steps:
-            copy_stream.wait_event(consumed)
-            with torch.cuda.stream(copy_stream):
-                stage[0].copy_(h_images, non_blocking=True)
-                stage[1].copy_(h_labels, non_blocking=True)
-                for dm, hm in zip(stage[2], h_masks):
-                    dm.copy_(hm, non_blocking=True)
-                staged.record(copy_stream)
-        step()
-        result_host.copy_(img.abs().mean().reshape(1), non_blocking=True)
+    e2e_pass(args.steps)
     t1.record()
     torch.cuda.synchronize()
     reducer.barrier()

@@ -10,7 +10,7 @@ import re
 import sys
 from collections import defaultdict
 
-KERNELS = ["conv_halo2_kernel", "conv_halo_kernel", "wgrad_halo_kernel", "conv_wgrad_kernel", "conv_fprop_kernel"]
+KERNELS = ["conv_stack3_kernel", "conv_halo2_kernel", "conv_halo_kernel", "wgrad_halo_kernel", "conv_wgrad_kernel", "conv_fprop_kernel"]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 

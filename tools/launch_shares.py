@@ -47,6 +47,17 @@ def main():
           (sum(v[0] for v in agg.values()), steps, total, total / steps))
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-62s n/step=%6.1f %10.1f us/step %5.1f%%  avg %7.1f" % (k, n / steps, us / steps, 100 * us / total, us / n))
+    fam = defaultdict(lambda: [0, 0.0])
+    for k, (n, us) in agg.items():
+        f = re.sub(r"<.*$", "", k)
+        fam[f][0] += n
+        fam[f][1] += us
+    print("\nby kernel family (template arguments merged):")
+    for k, (n, us) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:24]:
+        print("%-62s n/step=%6.1f %10.1f us/step %5.1f%%  avg %7.1f" % (k, n / steps, us / steps, 100 * us / total, us / n))
+    tensor = sum(us for k, (n, us) in fam.items() if k.startswith(("conv_", "wgrad_halo")) and "epilogue" not in k
+                 and "tanh" not in k)
+    print("tensor-core kernels: %.1f%% of the serialised kernel time" % (100 * tensor / total))
 
 
 if __name__ == "__main__":
