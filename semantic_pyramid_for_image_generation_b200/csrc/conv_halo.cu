@@ -493,6 +493,7 @@ int spyr_conv_halo_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     int dev = 0;
     SPYR_CHECK_CUDA(cudaGetDevice(&dev));
     SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (getenv("SPYR_CONV_SMS") != nullptr && atoi(getenv("SPYR_CONV_SMS")) > 0) num_sms = atoi(getenv("SPYR_CONV_SMS"));  // experiment
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   void (*kernel)(HaloMaps, HaloParams) = conv_halo_kernel<true, 0>;

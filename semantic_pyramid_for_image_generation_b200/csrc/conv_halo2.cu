@@ -532,6 +532,7 @@ int spyr_conv_halo2_launch(const spyr_conv_desc* d, cudaStream_t stream) {
     int dev = 0;
     SPYR_CHECK_CUDA(cudaGetDevice(&dev));
     SPYR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (getenv("SPYR_CONV_SMS") != nullptr && atoi(getenv("SPYR_CONV_SMS")) > 0) num_sms = atoi(getenv("SPYR_CONV_SMS"));  // experiment
   }
   const int total_pairs = (p.m_tiles / 2) * p.n_tiles;
   int pairs = num_sms / 2;
