@@ -24,7 +24,11 @@ build/test_conv_native: tests/native/test_conv_native.cu tests/native/halo_probe
 	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ tests/native/test_conv_native.cu tests/native/halo_probe.cu -L$(PKG) -lspyramid_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
 
 # developer probes behind the numbers in profiles/r01_mma_probe.txt and r01_tma_probe.txt
-probes: $(LIB) build/mma_probe build/tma_probe
+probes: $(LIB) build/mma_probe build/tma_probe build/pdl_probe
+
+build/pdl_probe: tests/native/pdl_probe.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $<
 
 build/mma_probe: tests/native/mma_probe.cu $(CSRC)/common.cuh
 	@mkdir -p build
