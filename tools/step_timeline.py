@@ -9,14 +9,20 @@ from semantic_pyramid_for_image_generation_b200.model_wrapper import ModelWrappe
 from semantic_pyramid_for_image_generation_b200.optim import FusedAdam
 
 out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.jsonl"
+from semantic_pyramid_for_image_generation_b200 import distributed
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+reducer = distributed.init_from_env("nccl") if world > 1 else None
 torch.manual_seed(0)
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", local)
 G = models.Generator(channels_factor=1).to(dev).train()
 D = models.Discriminator(channel_factor=1).to(dev).train()
 V = models.VGG16().to(dev).eval()
 w = ModelWrapper(G, D, None, None, vgg16=V, generator_optimizer=FusedAdam(G.parameters(), lr=1e-5),
-                 discriminator_optimizer=FusedAdam(D.parameters(), lr=1e-5), save_data_path="/tmp/spyr_tl")
-h_images, h_labels, h_masks = bench.host_batch(20, seed=0)
+                 discriminator_optimizer=FusedAdam(D.parameters(), lr=1e-5), save_data_path="/tmp/spyr_tl_%d" % rank,
+                 reducer=reducer)
+h_images, h_labels, h_masks = bench.host_batch(20, seed=rank)
 imgs, labs, masks = h_images.to(dev), h_labels.to(dev), [m.to(dev) for m in h_masks]
 for _ in range(3):
     w.training_step(imgs, labs, masks)
@@ -29,6 +35,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         cap()
     torch.cuda.synchronize()
+if rank != 0:
+    torch.distributed.destroy_process_group()
+    sys.exit(0)
 prof.export_chrome_trace("/tmp/trace.json")
 tr = json.load(open("/tmp/trace.json"))
 n = 0
@@ -40,3 +49,5 @@ with open(out_path, "w") as f:
                                 "grid": a.get("grid"), "block": a.get("block"), "smem": a.get("shared memory")}) + "\n")
             n += 1
 print("kernels", n)
+if world > 1:
+    torch.distributed.destroy_process_group()

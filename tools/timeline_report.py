@@ -61,6 +61,9 @@ for k, v in sorted(low_by_kernel.items(), key=lambda kv: -kv[1])[:25]:
 bs = collections.defaultdict(float)
 for e in step:
     bs[e["stream"]] += e["dur"]
+nccl = [e for e in step if "nccl" in e["name"].lower()]
+for e in nccl:
+    print("NCCL kernel at +%.3f ms: %.3f ms  grid %s  %s" % ((e["ts"] - t0) / 1e3, e["dur"] / 1e3, e["grid"], e["name"][:50]))
 print("per-stream kernel time (ms):", {k: round(v / 1e3, 2) for k, v in bs.items()})
 # coarse timeline: 0.25 ms slots with fill
 slot = 250.0
