@@ -45,7 +45,9 @@ int spyr_get_precision(void);
 #define SPYR_BN_BWD_PARTIAL_BYTES(C) ((long long)(4 * SPYR_REDUCE_BLOCKS + 4 * SPYR_REDUCE_BLOCKS) * 2 * (long long)(C) * 4)
 /* number of kernels launched through this library by the calling process (bench.py "gpu_launches") */
 long long spyr_launch_count(void);
-/* name of the tensor-core kernel the calling thread's last spyr_conv2d_fprop / spyr_conv2d_wgrad launched */
+/* name of the tensor-core kernel the calling thread's last spyr_conv2d_fprop / spyr_conv2d_wgrad launched:
+ * conv_stack3_kernel (Cout = 64, 3x3, maps >= 128 wide), conv_halo2_kernel (CTA pairs, Cout % 128 == 0 or 64),
+ * conv_halo_kernel (other maps >= 16x8), conv_fprop_kernel (small maps, split-K, FC), wgrad_halo_kernel, conv_wgrad_kernel */
 const char* spyr_last_conv_kernel(void);
 void spyr_launch_count_reset(void);
 
@@ -181,7 +183,7 @@ int spyr_nchw_to_nhwc(const float* src, const float* mask, float slope, void* ds
 int spyr_nhwc_to_nchw(const void* src, const float* gate_x, float slope, float* dst, int B, int C, int HW, void* stream);
 int spyr_maskgate(const void* f, const float* mask, void* out, long long npix, int C, void* stream);
 /* dst[t][n][k] = src[taps-1-t][k][n] (bf16): forward weight pack [tap][Cout=K][Cin=N] -> K-major operand of the input
- * gradient (taps flipped); lets 64-wide input gradients run on the CTA-pair kernel */
+ * gradient (taps flipped); lets 64-wide input gradients run on the row-stacked / CTA-pair kernels */
 int spyr_weight_transpose_flip(const void* src, void* dst, int taps, int K, int N, void* stream);
 
 /* ---- VGG-16 fine-tuning (vgg_16_train.py:134-165): what the frozen-encoder path did not need ----
