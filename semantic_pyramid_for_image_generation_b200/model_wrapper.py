@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from . import misc
+from . import engine, misc
 from .lossfunction import (DiversityLoss, LSGANDiscriminatorLoss, LSGANGeneratorLoss, SemanticReconstructionLoss,
                            lsgan_term)
 from .models import VGG16
@@ -103,11 +103,20 @@ class ModelWrapper(object):
         main, side, third = torch.cuda.current_stream(), self._second_stream(device), self._second_stream(device, 1)
         if side is not None:
             side.wait_stream(main)
+            prep = self._second_stream(device, 2)
+            if prep is not None and hasattr(G, "_sn") and os.environ.get("SPYR_SN_PREFETCH", "1") != "0":
+                # G's spectral-norm pass does not need the VGG features: next to VGG(real) instead of behind it
+                prep.wait_stream(main)
+                with torch.no_grad(), torch.cuda.stream(prep):
+                    engine.prepare_generator(G)
         with torch.no_grad(), torch.cuda.stream(side if side is not None else main):
             features_real = V(images_real)
             if z_d is None:
                 z_d = torch.randn((batch, self.latent_dimensions), dtype=torch.float32, device=device)
-            images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
+            try:
+                images_fake = G(input=z_d, features=features_real, masks=masks, class_id=labels.float())
+            finally:
+                G.__dict__.pop("_sn_prepared", None)  # never leave a prepared state behind for a later forward
         if side is None or type(self.discriminator_loss) is not LSGANDiscriminatorLoss:  # subclasses may override forward
             # a user-supplied loss couples the two predictions: D(real) still overlaps VGG -> G, one joint backward
             prediction_real = D(images_real, labels)
