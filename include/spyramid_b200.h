@@ -272,6 +272,10 @@ int spyr_bn_bwd_reduce(const void* g, const void* x, const float* mean_rstd, con
                        int B, int H, int W, int C, void* stream);
 int spyr_bn_bwd_finalize(const float* S, int B, int C, float count, const float* scale_ptr, int row_stride, const int* cls,
                          float* M /* [2C] */, float* d_scale, float* d_shift, void* stream);
+/* the parameter-gradient half of spyr_bn_bwd_finalize on its own (a leaf of the backward pass: d_scale[row(b)][c] += S2[b,c],
+ * d_shift likewise with S1, samples in order); spyr_bn_bwd_finalize with d_scale == NULL computes the channel means only */
+int spyr_bn_bwd_params(const float* S, int B, int C, int row_stride, const int* cls, float* d_scale, float* d_shift,
+                       void* stream);
 int spyr_bn_bwd_apply(const void* gy, const void* x, const float* mean_rstd, const float* scale_ptr, int row_stride,
                       const int* cls, const float* M, const void* residual, void* gx, int B, int H, int W, int C, int x_up2,
                       void* stream); /* x_up2: gy/gx at 2H x 2W, xhat from up2(x); H, W are x's dims */

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "spyr_bn_act": [P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_bn_bwd_reduce": [P, P, P, P, P, c_int, P, c_float, c_int, P, P, c_int, c_int, c_int, c_int, P],
     "spyr_bn_bwd_finalize": [P, c_int, c_int, c_float, P, c_int, P, P, P, P, P],
+    "spyr_bn_bwd_params": [P, c_int, c_int, c_int, P, P, P, P],
     "spyr_bn_bwd_apply": [P, P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],  # B,H,W,C,x_up2
     "spyr_up2_bwd": [P, P, c_int, c_int, c_int, c_int, P],
     "spyr_argmax_rows": [P, c_int, c_int, c_int, P, P],

@@ -183,8 +183,10 @@ def _cbn_backward(cbn, ga, grad, x, mr, cls, g, mode, residual=None):
          gy.data_ptr() if mode else None, S.data_ptr(), B, H, W, Cc)
     M = torch.empty(2 * Cc, dtype=F32, device=x.device)
     ge = ga.ptr(grad, emb)
-    call("spyr_bn_bwd_finalize", S.data_ptr(), B, Cc, float(B * H * W), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(), ge,
-         ge + 4 * Cc)
+    call("spyr_bn_bwd_finalize", S.data_ptr(), B, Cc, float(B * H * W), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(), None,
+         None)
+    # the gain / bias gradients of the class rows are leaves: off the reduce -> finalize -> apply chain
+    ops.LEAF.run([S, cls], "spyr_bn_bwd_params", S.data_ptr(), B, Cc, 2 * Cc, cls.data_ptr(), ge, ge + 4 * Cc)
     gx = ops.act_like(x)
     call("spyr_bn_bwd_apply", gy.data_ptr(), x.data_ptr(), mr.data_ptr(), sp, 2 * Cc, cls.data_ptr(), M.data_ptr(),
          ptr(residual), gx.data_ptr(), B, H, W, Cc, 0)
@@ -375,8 +377,8 @@ def generator_backward(G, ctx, g_img):
     call("spyr_bn_bwd_reduce", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, bp, 0, None, LRELU, mode, None,
          S.data_ptr(), B, hs, ws, c5)
     M = torch.empty(2 * c5, dtype=F32, device=dev)
-    call("spyr_bn_bwd_finalize", S.data_ptr(), B, c5, float(B * 4 * H * W), wp, 0, None, M.data_ptr(),
-         ga.ptr(grad, bn.weight), ga.ptr(grad, bn.bias))
+    call("spyr_bn_bwd_finalize", S.data_ptr(), B, c5, float(B * 4 * H * W), wp, 0, None, M.data_ptr(), None, None)
+    ops.LEAF.run([S], "spyr_bn_bwd_params", S.data_ptr(), B, c5, 0, None, ga.ptr(grad, bn.weight), ga.ptr(grad, bn.bias))
     g_hi = ops.act_like(g_pre)
     call("spyr_bn_bwd_apply", g_pre.data_ptr(), xs.data_ptr(), mr.data_ptr(), wp, 0, None, M.data_ptr(), None,
          g_hi.data_ptr(), B, hs, ws, c5, 0 if xu is not None else 1)
