@@ -173,6 +173,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nb, 
   const int lane = threadIdx.x & 31;
   double s1 = 0.0, s2 = 0.0;
   if (c < C && training) {
+    // up to 296 partial vectors, ~10 per lane, each load a different line: keep several in flight (the adds stay in order)
+#pragma unroll 5
     for (int b = lane; b < nb; b += 32) {
       s1 += __ldcg(partials + (size_t)b * 2 * C + c);
       s2 += __ldcg(partials + (size_t)b * 2 * C + C + c);
@@ -549,21 +551,32 @@ __global__ void up2_bwd_kernel(const ActT<S> g, const ActT<S> out, int B, int H,
 }
 
 // class index of each one-hot row (class_id.argmax(dim=-1), models.py:151,501); first maximum wins like torch
+// One warp per row: every lane keeps the first maximum of its strided elements, a butterfly picks the larger value and, on
+// ties, the smaller index.  (A single thread scanning the 365 entries took 12-24 us at the head of every G / D forward.)
 template <typename T>
 __global__ void argmax_rows_kernel(const T* __restrict__ onehot, int n, int* __restrict__ out) {
   const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
-    int best = 0;
-    T m = onehot[(size_t)b * n];
-    for (int i = 1; i < n; ++i) {
-      const T v = onehot[(size_t)b * n + i];
-      if (v > m) {
-        m = v;
-        best = i;
-      }
+  const int lane = threadIdx.x;
+  const T* row = onehot + (size_t)b * n;
+  T m = row[0];
+  int best = 0;
+  for (int i = lane; i < n; i += 32) {
+    const T v = row[i];
+    if (v > m || (v == m && i < best)) {
+      m = v;
+      best = i;
     }
-    out[b] = best;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (om > m || (om == m && ob < best)) {
+      m = om;
+      best = ob;
+    }
+  }
+  if (lane == 0) out[b] = best;
 }
 
 struct Threads {

@@ -649,6 +649,20 @@ def test_conv_64_channel_rows_stacked(ops, shape):
     assert torch.equal(ops.act_value(got), ops.act_value(again))
 
 
+def test_argmax_rows_first_maximum(ops):
+    """class_id.argmax(dim=-1) (models.py:151,501) for int64 one-hot labels and float rows; ties resolve to the first
+    maximum like torch."""
+    g = gen(41)
+    B, n = 20, 365
+    idx = torch.randint(0, n, (B,), generator=g)
+    onehot = F.one_hot(idx, n).long()
+    assert torch.equal(ops.argmax_rows(onehot.cuda()).cpu().long(), idx)
+    x = torch.randint(0, 5, (B, n), generator=g).float()  # many ties
+    x[3] = 0.0
+    x[4, n - 1] = 9.0
+    assert torch.equal(ops.argmax_rows(x.cuda()).cpu().long(), x.argmax(dim=-1))
+
+
 def test_reductions_are_bit_reproducible(ops):
     """No floating-point atomics: split-K convolutions, weight gradients, bias column sums, BN statistics and the stencil
     gradient give bit-identical results on repeated launches (the small-map split-K and every weight gradient used
