@@ -201,6 +201,7 @@ __global__ void dhead_out_bwd_kernel(const float* __restrict__ g, const float* _
   float cls_acc = 0.f;
   for (int k = threadIdx.x; k < E; k += blockDim.x) {
     float gf = 0.f;
+#pragma unroll 4  // read-only: four samples' loads (g, idx -> embedding row) in flight, sums stay in batch order
     for (int q = 0; q < B; ++q) {
       const float gj = g[((size_t)q * B + r) * E + k];  // i = q, j = r
       gf += gj * emb_w[(size_t)idx[q] * E + k] * inv;
@@ -219,6 +220,7 @@ __global__ void dhead_out_bwd_kernel(const float* __restrict__ g, const float* _
         float ge = 0.f;
         for (int r2 = r; r2 < B; ++r2) {
           if (idx[r2] != cls_r) continue;
+#pragma unroll 4
           for (int q = 0; q < B; ++q) ge += g[((size_t)r2 * B + q) * E + k] * feat[(size_t)q * E + k];  // i = r2, j = q
         }
         g_embw[(size_t)cls_r * E + k] += ge;
